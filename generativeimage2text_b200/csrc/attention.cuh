@@ -1,0 +1,387 @@
+// Multi-head attention kernels (head dim 64).
+//
+// flash_attn_kernel : non-causal softmax(q k^T / 8) v over S keys for every (batch, head); used by the
+//   ViT blocks (reference layers/CLIP/model.py:189-197 -> nn.MultiheadAttention -> SDPA, no mask) and by
+//   the one-off image-row pass of the decoder (image rows attend image rows only, reference
+//   layers/decoder.py:119-120; layers/bert/modeling_bert.py:41-47,138-152).  Online-softmax over 64-key
+//   chunks, cp.async double buffering, warp-level bf16 tensor-core MMAs with fp32 accumulation.
+//
+// decode_attn_kernel : one new text row per sequence against [image K/V || text K/V] (the KV-cached form of
+//   reference layers/decoder.py:121-123 + modeling_bert.py:124-152).  Pure HBM streaming: every K/V row is
+//   read once with 128-bit loads; image K/V are shared by the beams of an image; the new token's K/V are
+//   appended to the text cache by the same kernel.
+#pragma once
+#include "ptx.cuh"
+#include "rowops.cuh"
+
+namespace gitb200 {
+
+struct AttnParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  __nv_bfloat16* out;
+  int B, S, H;
+  long long q_rs, kv_rs, q_bs, kv_bs, o_rs, o_bs;  // row / batch strides in elements
+  float scale_log2;                                 // (1/sqrt(64)) * log2(e)
+};
+
+__device__ __forceinline__ void attn_load_tile(uint32_t smem_base, const __nv_bfloat16* g, long long row_stride,
+                                               int row0, int nrows, int S, int tid, int nthreads) {
+  for (int idx = tid; idx < nrows * 8; idx += nthreads) {
+    const int r = idx >> 3;
+    const int c = idx & 7;
+    const bool valid = (row0 + r) < S;
+    const int gr = valid ? (row0 + r) : (S - 1);
+    const __nv_bfloat16* src = g + static_cast<long long>(gr) * row_stride + c * 8;
+    cp_async_16(smem_base + r * 128 + ((c ^ (r & 7)) << 4), src, valid);
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) flash_attn_kernel(const AttnParams p) {
+  constexpr int QROWS = NW * 16;
+  constexpr int KC = 64;
+  __shared__ __align__(128) uint8_t sQ[QROWS * 128];
+  __shared__ __align__(128) uint8_t sK[2][KC * 128];
+  __shared__ __align__(128) uint8_t sV[2][KC * 128];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int q_row0 = blockIdx.x * QROWS;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const __nv_bfloat16* qg = p.q + b * p.q_bs + h * 64;
+  const __nv_bfloat16* kg = p.k + b * p.kv_bs + h * 64;
+  const __nv_bfloat16* vg = p.v + b * p.kv_bs + h * 64;
+  const int nchunks = (p.S + KC - 1) / KC;
+
+  attn_load_tile(smem_u32(sQ), qg, p.q_rs, q_row0, QROWS, p.S, tid, NW * 32);
+  attn_load_tile(smem_u32(sK[0]), kg, p.kv_rs, 0, KC, p.S, tid, NW * 32);
+  attn_load_tile(smem_u32(sV[0]), vg, p.kv_rs, 0, KC, p.S, tid, NW * 32);
+  cp_async_commit();
+
+  uint32_t qa[4][4];
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  }
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) {
+      attn_load_tile(smem_u32(sK[buf ^ 1]), kg, p.kv_rs, (c + 1) * KC, KC, p.S, tid, NW * 32);
+      attn_load_tile(smem_u32(sV[buf ^ 1]), vg, p.kv_rs, (c + 1) * KC, KC, p.S, tid, NW * 32);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (c == 0) {
+      const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int chunk = 2 * kk + (lane >> 4);
+        ldmatrix_x4(qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], smem_u32(sQ) + row * 128 + ((chunk ^ (row & 7)) << 4));
+      }
+    }
+    // ---- S = Q K^T for this chunk -------------------------------------------------------------
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const int krow = 8 * j + (lane & 7);
+#pragma unroll
+      for (int kk2 = 0; kk2 < 2; ++kk2) {
+        const int chunk = 4 * kk2 + (lane >> 3);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(b0, b1, b2, b3, smem_u32(sK[buf]) + krow * 128 + ((chunk ^ (krow & 7)) << 4));
+        mma_bf16_16816(s[j], qa[2 * kk2], b0, b1);
+        mma_bf16_16816(s[j], qa[2 * kk2 + 1], b2, b3);
+      }
+    }
+    // ---- mask the tail, online softmax ---------------------------------------------------------
+    const int key0 = c * KC + 2 * (lane & 3);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = key0 + 8 * j;
+      if (key >= p.S) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (key + 1 >= p.S) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+    }
+    float corr[2], m_new[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      m_new[i] = fmaxf(m_run[i], mx[i]);
+      corr[i] = exp2f((m_run[i] - m_new[i]) * p.scale_log2);
+      m_run[i] = m_new[i];
+      l_run[i] *= corr[i];
+    }
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f((s[j][0] - m_new[0]) * p.scale_log2);
+      const float p1 = exp2f((s[j][1] - m_new[0]) * p.scale_log2);
+      const float p2 = exp2f((s[j][2] - m_new[1]) * p.scale_log2);
+      const float p3 = exp2f((s[j][3] - m_new[1]) * p.scale_log2);
+      l_run[0] += p0 + p1;
+      l_run[1] += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      o[j][0] *= corr[0];
+      o[j][1] *= corr[0];
+      o[j][2] *= corr[1];
+      o[j][3] *= corr[1];
+    }
+    // ---- O += P V -------------------------------------------------------------------------------
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int vrow = 16 * kk + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int chunk = 2 * jj + (lane >> 4);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(sV[buf]) + vrow * 128 + ((chunk ^ (vrow & 7)) << 4));
+        mma_bf16_16816(o[2 * jj], pa[kk], b0, b1);
+        mma_bf16_16816(o[2 * jj + 1], pa[kk], b2, b3);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 1);
+    l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 2);
+  }
+  const float inv0 = 1.0f / l_run[0];
+  const float inv1 = 1.0f / l_run[1];
+  const int r0 = q_row0 + warp * 16 + (lane >> 2);
+  const int r1 = r0 + 8;
+  __nv_bfloat16* og = p.out + b * p.o_bs + h * 64 + 2 * (lane & 3);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (r0 < p.S)
+      *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r0) * p.o_rs + 8 * j) = pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+    if (r1 < p.S)
+      *reinterpret_cast<uint32_t*>(og + static_cast<long long>(r1) * p.o_rs + 8 * j) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct DecAttnParams {
+  const float* qkv;                // [R, 3*D] fp32, bias included (q | k | v)
+  const __nv_bfloat16* img_k;      // [B, M, D]
+  const __nv_bfloat16* img_v;
+  __nv_bfloat16* txt_k;            // [R, T_alloc, D]
+  __nv_bfloat16* txt_v;
+  const int* src_row;              // [R, T_alloc] physical row holding text position j of logical row r (null = r)
+  __nv_bfloat16* ctx;              // [R, D]
+  int B, M, T_alloc, D;
+  const StepState* state;          // text position = state->pos (or pos_fixed when null)
+  int pos_fixed;
+};
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p) {
+  if (p.state != nullptr && p.state->finished) return;
+  extern __shared__ float dyn_smem[];
+  const int pos = (p.state != nullptr) ? p.state->pos : p.pos_fixed;
+  const int n_txt = pos + 1;
+  const int Sk = p.M + n_txt;
+  float* sc = dyn_smem;  // [NQ][Sk]
+  __shared__ float q_s[NQ][64];
+  __shared__ float inv_sum[NQ];
+  __shared__ float red[4][NQ][64];
+
+  const int h = blockIdx.x;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int D = p.D;
+
+  // ---- phase 0: q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V ----
+  for (int qi = 0; qi < NQ; ++qi) {
+    const int r = b * NQ + qi;
+    const float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
+    if (tid < 64) {
+      q_s[qi][tid] = row[tid] * 0.125f;
+      p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(row[D + tid]);
+    } else {
+      const int d = tid - 64;
+      p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(row[2 * D + d]);
+    }
+  }
+  __syncthreads();
+
+  const int grp = tid >> 3;  // 16 key groups
+  const int gl = tid & 7;    // 8 lanes x 8 dims
+  float qreg[NQ][8];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+    for (int d = 0; d < 8; ++d) qreg[qi][d] = q_s[qi][gl * 8 + d];
+
+  // ---- phase 1: scores ---------------------------------------------------------------------------
+  {
+    const __nv_bfloat16* kb = p.img_k + static_cast<long long>(b) * p.M * D + h * 64 + gl * 8;
+    for (int base = 0; base < p.M; base += 64) {  // uniform trip count: the shuffles below stay converged
+      const int s0 = base + grp;
+      uint4 u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int s = s0 + 16 * i;
+        u[i] = (s < p.M) ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int s = s0 + 16 * i;
+        float f[8];
+        bf16x8_to_f32(u[i], f);
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], f[d], a);
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          a += __shfl_xor_sync(0xffffffffu, a, 4);
+          if (gl == 0 && s < p.M) sc[qi * Sk + s] = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+      const int r = b * NQ + qi;
+      for (int j0 = 0; j0 < n_txt; j0 += 16) {  // uniform trip count: shuffles stay converged
+        const int j = j0 + grp;
+        float a = 0.f;
+        if (j < n_txt) {
+          const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
+          const uint4 u = *reinterpret_cast<const uint4*>(p.txt_k + (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8);
+          float f[8];
+          bf16x8_to_f32(u, f);
+#pragma unroll
+          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], f[d], a);
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (gl == 0 && j < n_txt) sc[qi * Sk + p.M + j] = a;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: softmax (one warp per query) -------------------------------------------------------
+  {
+    const int w = tid >> 5;
+    const int lane = tid & 31;
+    for (int qi = w; qi < NQ; qi += 4) {
+      float mx = -INFINITY;
+      for (int s = lane; s < Sk; s += 32) mx = fmaxf(mx, sc[qi * Sk + s]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int s = lane; s < Sk; s += 32) {
+        const float e = __expf(sc[qi * Sk + s] - mx);
+        sc[qi * Sk + s] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) inv_sum[qi] = 1.0f / sum;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: ctx = P V -----------------------------------------------------------------------------
+  float acc[NQ][8];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[qi][d] = 0.f;
+  {
+    const __nv_bfloat16* vb = p.img_v + static_cast<long long>(b) * p.M * D + h * 64 + gl * 8;
+    for (int base = 0; base < p.M; base += 64) {
+      const int s0 = base + grp;
+      uint4 u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int s = s0 + 16 * i;
+        u[i] = (s < p.M) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int s = s0 + 16 * i;
+        if (s < p.M) {
+          float f[8];
+          bf16x8_to_f32(u[i], f);
+#pragma unroll
+          for (int qi = 0; qi < NQ; ++qi) {
+            const float pw = sc[qi * Sk + s];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) acc[qi][d] = fmaf(pw, f[d], acc[qi][d]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+      const int r = b * NQ + qi;
+      for (int j = grp; j < n_txt; j += 16) {
+        const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
+        const uint4 u = *reinterpret_cast<const uint4*>(p.txt_v + (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8);
+        float f[8];
+        bf16x8_to_f32(u, f);
+        const float pw = sc[qi * Sk + p.M + j];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[qi][d] = fmaf(pw, f[d], acc[qi][d]);
+      }
+    }
+  }
+  // reduce the 4 key groups of a warp, then the 4 warps
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      float a = acc[qi][d];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      acc[qi][d] = a;
+    }
+  {
+    const int w = tid >> 5;
+    const int lane = tid & 31;
+    if (lane < 8) {
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) red[w][qi][lane * 8 + d] = acc[qi][d];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < NQ * 64; i += 128) {
+    const int qi = i >> 6;
+    const int d = i & 63;
+    const float v = (red[0][qi][d] + red[1][qi][d]) + (red[2][qi][d] + red[3][qi][d]);
+    p.ctx[static_cast<long long>(b * NQ + qi) * D + h * 64 + d] = __float2bfloat16_rn(v * inv_sum[qi]);
+  }
+}
+
+}  // namespace gitb200

@@ -1,0 +1,281 @@
+// C[M,N] = A[M,K] * B[N,K]^T with bf16 operands (both K-major: exactly the layout of an activation
+// matrix and of an nn.Linear weight), fp32 accumulation in TMEM, fused epilogues.
+//
+// One persistent, warp-specialised sm_100a kernel:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B-swizzled [rows x 64] bf16 tiles, STAGES-deep ring)
+//   warp 1   : UMMA issuer   (one lane issues tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld -> bias / activation / residual -> global stores)
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Two epilogue shapes:
+//   normal     : out[row_map(m)][n] (+bias[n]) (+act) (+resid[m][n]); N may be split into up to three equal
+//                column segments with their own base pointers (QKV -> q scratch / K cache / V cache).
+//   transposed : "swap-AB" for the skinny decode-step GEMMs: A = weight [features, K], B = activations
+//                [rows<=BN, K]; out[n][m] (+bias[m]) (+act), optionally accumulated with fp32 atomics when
+//                the K dimension is split over CTAs so a handful of rows still spreads over many SMs.
+#pragma once
+#include "ptx.cuh"
+
+namespace gitb200 {
+
+struct GemmParams {
+  int M, N, K;
+  int k_splits;
+  int transposed;
+  int atomic;
+  int act;
+  int out_bf16;
+  const float* bias;
+  const float* resid;  // normal mode only, fp32, identity row mapping
+  long long ld_resid;
+  void* out[3];
+  long long ldo[3];
+  long long batch_stride[3];  // in rows
+  int seg_n;                  // segment width (normal mode); N for a single segment
+  int rows_per_batch;         // row map: m -> (m / rpb) * batch_stride[seg] + (m % rpb) + row_offset
+  int row_offset;
+  const int* skip;            // device flag: non-zero -> the whole launch is a no-op (finished decode)
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
+  static_assert((2 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier area");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const GemmParams p) {
+  using C = GemmCfg<BN>;
+  if (p.skip != nullptr && *p.skip != 0) return;  // uniform over the grid
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (p.M + C::BM - 1) / C::BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int kb_total = (p.K + C::BK - 1) / C::BK;
+  const int kb_per = (kb_total + p.k_splits - 1) / p.k_splits;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * p.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / mn_tiles;
+        const int rem = tile - split * mn_tiles;
+        const int m_blk = rem / n_tiles;
+        const int n_blk = rem - m_blk * n_tiles;
+        const int kb0 = split * kb_per;
+        const int kb1 = min(kb_total, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full[stage], kb * C::BK, m_blk * C::BM);
+          tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full[stage], kb * C::BK, n_blk * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ UMMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(C::BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int accum = 0;
+      uint32_t accum_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / mn_tiles;
+        const int kb0 = split * kb_per;
+        const int kb1 = min(kb_total, kb0 + kb_per);
+        mbar_wait(&tempty[accum], accum_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + accum * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < C::BK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[accum]);  // accumulator complete -> epilogue
+        accum ^= 1;
+        if (accum == 0) accum_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ----------------------------------
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int accum = 0;
+    uint32_t accum_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile / mn_tiles;
+      const int rem = tile - split * mn_tiles;
+      const int m_blk = rem / n_tiles;
+      const int n_blk = rem - m_blk * n_tiles;
+      mbar_wait(&tfull[accum], accum_phase);
+      tc_fence_after();
+      const int row = m_blk * C::BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN + c * 32, r);
+        tmem_ld_wait();
+        if (!p.transposed) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[4 * j + 0] += b4.x;
+              v[4 * j + 1] += b4.y;
+              v[4 * j + 2] += b4.z;
+              v[4 * j + 3] += b4.w;
+            }
+          }
+          if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (row_ok) {
+            if (p.resid != nullptr) {
+              const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ld_resid + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r4 = rp[j];
+                v[4 * j + 0] += r4.x;
+                v[4 * j + 1] += r4.y;
+                v[4 * j + 2] += r4.z;
+                v[4 * j + 3] += r4.w;
+              }
+            }
+            const int seg = n0 / p.seg_n;
+            const int nn = n0 - seg * p.seg_n;
+            const int b = row / p.rows_per_batch;
+            const int s = row - b * p.rows_per_batch;
+            const long long orow = static_cast<long long>(b) * p.batch_stride[seg] + s + p.row_offset;
+            if (p.out_bf16) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + orow * p.ldo[seg] + nn);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                op[j] = o;
+              }
+            } else {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + orow * p.ldo[seg] + nn);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        } else {
+          // transposed: lane = output feature `row`, register j = activation row n0 + j
+          const float bv = (p.bias != nullptr && row_ok && split == 0) ? __ldg(p.bias + row) : 0.0f;
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int rr = n0 + j;
+              if (rr < p.N) {
+                float v = __uint_as_float(r[j]) + bv;
+                v = apply_act(v, p.act);
+                const long long off = static_cast<long long>(rr) * p.ldo[0] + row;
+                if (p.atomic) {
+                  atomicAdd(reinterpret_cast<float*>(p.out[0]) + off, v);
+                } else if (p.out_bf16) {
+                  reinterpret_cast<__nv_bfloat16*>(p.out[0])[off] = __float2bfloat16_rn(v);
+                } else {
+                  reinterpret_cast<float*>(p.out[0])[off] = v;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[accum]);
+      accum ^= 1;
+      if (accum == 0) accum_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+}  // namespace gitb200

@@ -1,0 +1,805 @@
+// libgitb200.so -- C ABI + host-side engine of the B200-native GIT captioning hot path.
+// See include/gitb200.h for the contract of every entry point and the reference function it replaces.
+//
+// Device data layout (all engine-owned, HBM resident):
+//   weights      : GEMM operands bf16 [out, in] (the nn.Linear layout is already K-major), biases /
+//                  LayerNorm / embeddings fp32; decoder q,k,v fused to one [2304, 768] matrix; patch kernel
+//                  flattened to [d, 3*p*p] zero-padded to a multiple of 64 columns.
+//   encoder      : residual stream x fp32 [NI*L, d]; GEMM A operands (LN output, attention context, MLP
+//                  hidden) bf16 row-major; packed qkv bf16 [NI*L, 3d].
+//   image K/V    : bf16 [layer][k|v][B][M][768]  (token-major rows: a decode-step reader streams contiguous
+//                  1536-byte rows; written once by the prefill QKV GEMM epilogue, shared by all beams).
+//   text K/V     : bf16 [layer][k|v][rows][T_alloc][768] + int32 src_row[rows][T_alloc] indirection for beams.
+//   decode step  : fp32 row state [rows, 768], bf16 copy for the GEMMs, fp32 qkv / logits.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/gitb200.h"
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+#include "rowops.cuh"
+#include "search.cuh"
+
+using namespace gitb200;
+typedef __nv_bfloat16 bf16;
+
+#define GITB200_ABI_VERSION 1
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct EncLayer {
+  DevBuf wqkv, bqkv, wo, bo, ln1g, ln1b, ln2g, ln2b, w1, b1, w2, b2;
+};
+struct DecLayer {
+  DevBuf wqkv, bqkv, wo, bo, lnag, lnab, w1, b1, w2, b2, lnog, lnob;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int box_rows;
+  bool operator<(const TmapKey& o) const {
+    if (ptr != o.ptr) return ptr < o.ptr;
+    if (rows != o.rows) return rows < o.rows;
+    if (cols != o.cols) return cols < o.cols;
+    if (ld != o.ld) return ld < o.ld;
+    return box_rows < o.box_rows;
+  }
+};
+
+struct gitb200_engine {
+  gitb200_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  int64_t launches = 0;
+  bool use_graph = true;
+
+  // derived geometry
+  int g = 0, L = 0, Kpatch = 0, Kp = 0, d = 0, D = 0, F = 0, V = 0;
+
+  // weights
+  DevBuf w_patch, cls, pos_emb, lnpre_g, lnpre_b, lnpost_g, lnpost_b;
+  std::vector<EncLayer> enc;
+  DevBuf w_vp, b_vp, lnvp_g, lnvp_b, words_f32, words_bf16, positions, lnemb_g, lnemb_b, out_bias, temb;
+  std::vector<DecLayer> dec;
+  std::set<std::string> seen;
+  bool finalized = false;
+
+  // workspaces
+  DevBuf x, h, qkv, ctx, u, feats, feats_f32;               // encoder
+  DevBuf pt, pxd, phd, pq, pctx, pu;                        // prefill
+  DevBuf img_kv, txt_kv, src_row[2];                        // caches
+  DevBuf xd_t, hd_t, qkv_t, ctx_t, t_t, u_t, logits;        // decode step
+  DevBuf state, next_token, logprob_sum, tokens_i64, stage_img, stage_tok, stage_lp, prefix_dev;
+  DevBuf beam_ws;                                           // beam-search bookkeeping (search.cuh)
+  int cur_B = 0, cur_frames = 0, cur_M = 0, cur_beam = 1, T_alloc = 0, cur_rows = 0, cur_src = 0;
+
+  EncodeTiledFn encode_tiled = nullptr;
+  std::map<TmapKey, CUtensorMap> tmaps;
+
+  // decode-step graph cache
+  cudaGraphExec_t step_graph = nullptr;
+  std::vector<long long> step_graph_key;
+  int64_t launches_per_step = 0;
+};
+
+static int fail(gitb200_engine* h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return 1;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKL(h_, what)                                                                                \
+  do {                                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                                             \
+    if (e_ != cudaSuccess) return fail(h_, "launch %s failed: %s", what, cudaGetErrorString(e_));    \
+    (h_)->launches++;                                                                                \
+  } while (0)
+#define TRY(expr)                 \
+  do {                            \
+    int rc_ = (expr);             \
+    if (rc_ != 0) return rc_;     \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors
+// ------------------------------------------------------------------------------------------------
+static int load_encode_fn(gitb200_engine* h) {
+  if (h->encode_tiled) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr)
+    return fail(h, "cuTensorMapEncodeTiled not available from the driver: %s", cudaGetErrorString(e));
+  h->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows x 64] swizzle-128B.
+static int get_tmap(gitb200_engine* h, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                    CUtensorMap* out) {
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  auto it = h->tmaps.find(key);
+  if (it != h->tmaps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  TRY(load_encode_fn(h));
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(h, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ptr=%p ld=%lld)", ptr, ld);
+  CUtensorMap m;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = h->encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%d)",
+                                     static_cast<int>(r), rows, cols, ld, box_rows);
+  if (h->tmaps.size() > 4096) h->tmaps.clear();
+  h->tmaps[key] = m;
+  *out = m;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launcher
+// ------------------------------------------------------------------------------------------------
+struct GemmCall {
+  const bf16* A = nullptr;  // [M, K] (kernel operand A: 128-row tiles)
+  long long lda = 0;
+  const bf16* B = nullptr;  // [N, K] (kernel operand B: BN-row tiles)
+  long long ldb = 0;
+  GemmParams p{};
+  int bn = 0;               // 0 = heuristic
+};
+
+template <int BN>
+static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
+  using C = GemmCfg<BN>;
+  static bool attr_set[64] = {false};
+  if (!attr_set[h->device & 63]) {
+    CK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  CUtensorMap ta, tb;
+  TRY(get_tmap(h, c.A, c.p.M, c.p.K, c.lda, 128, &ta));
+  TRY(get_tmap(h, c.B, c.p.N, c.p.K, c.ldb, BN, &tb));
+  const int m_tiles = (c.p.M + 127) / 128;
+  const int n_tiles = (c.p.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles * c.p.k_splits;
+  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  gemm_bf16_tcgen05<BN><<<grid, 256, C::SMEM_BYTES, st>>>(ta, tb, c.p);
+  CKL(h, "gemm_bf16_tcgen05");
+  return 0;
+}
+
+static int pick_bn(const gitb200_engine* h, int M, int N, bool transposed) {
+  if (transposed) return N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int m_tiles = (M + 127) / 128;
+  int best = 256;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (N % bn != 0 && N > bn) continue;
+    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+    const long long waves = (tiles + h->num_sms - 1) / h->num_sms;
+    // per-tile cost ~ bn (MMA time) + fixed overhead; narrower tiles pay relatively more smem traffic
+    const double cost = static_cast<double>(waves) * (bn + 24.0) * (bn == 128 ? 1.08 : 1.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static int launch_gemm(gitb200_engine* h, GemmCall c, cudaStream_t st) {
+  GemmParams& p = c.p;
+  if (p.k_splits < 1) p.k_splits = 1;
+  const int kb_total = (p.K + 63) / 64;
+  if (p.k_splits > kb_total) p.k_splits = kb_total;
+  {
+    const int kb_per = (kb_total + p.k_splits - 1) / p.k_splits;
+    p.k_splits = (kb_total + kb_per - 1) / kb_per;  // no empty split
+  }
+  if (p.seg_n <= 0) p.seg_n = p.N;
+  if (p.rows_per_batch <= 0) {
+    p.rows_per_batch = p.M;
+    for (int i = 0; i < 3; ++i) p.batch_stride[i] = p.M;
+  }
+  if (!p.transposed && (p.N % 32 != 0 || p.seg_n % 32 != 0))
+    return fail(h, "gemm: N and segment width must be multiples of 32 (N=%d seg=%d)", p.N, p.seg_n);
+  if (p.atomic && !p.transposed) return fail(h, "gemm: atomic accumulation is only implemented for the transposed epilogue");
+  if (p.k_splits > 1 && !p.atomic) return fail(h, "gemm: k_splits > 1 needs the atomic epilogue");
+  const int bn = c.bn > 0 ? c.bn : pick_bn(h, p.M, p.N, p.transposed != 0);
+  switch (bn) {
+    case 64: return launch_gemm_bn<64>(h, c, st);
+    case 128: return launch_gemm_bn<128>(h, c, st);
+    case 192: return launch_gemm_bn<192>(h, c, st);
+    case 256: return launch_gemm_bn<256>(h, c, st);
+    default: return fail(h, "gemm: unsupported tile width %d", bn);
+  }
+}
+
+// Plain C = A W^T (+bias)(+act)(+resid) -> out (fp32 or bf16), identity row map.
+static GemmCall gemm_plain(const bf16* A, long long lda, const bf16* W, long long ldw, int M, int N, int K,
+                           const float* bias, int act, const float* resid, void* out, bool out_bf16) {
+  GemmCall c;
+  c.A = A; c.lda = lda; c.B = W; c.ldb = ldw;
+  c.p.M = M; c.p.N = N; c.p.K = K; c.p.k_splits = 1;
+  c.p.bias = bias; c.p.act = act; c.p.resid = resid; c.p.ld_resid = N;
+  c.p.out[0] = out; c.p.ldo[0] = N; c.p.out_bf16 = out_bf16 ? 1 : 0;
+  c.p.seg_n = N;
+  return c;
+}
+// Skinny decode-step GEMM: out[r][f] = sum_k X[r][k] W[f][k] (+bias[f]) (+act) -- swap-AB, transposed epilogue.
+static GemmCall gemm_skinny(const bf16* X, long long ldx, const bf16* W, long long ldw, int rows, int feats, int K,
+                            const float* bias, int act, void* out, long long ldo, bool out_bf16, int k_splits,
+                            const int* skip) {
+  GemmCall c;
+  c.A = W; c.lda = ldw; c.B = X; c.ldb = ldx;
+  c.p.M = feats; c.p.N = rows; c.p.K = K; c.p.k_splits = k_splits;
+  c.p.transposed = 1; c.p.atomic = k_splits > 1 ? 1 : 0;
+  c.p.bias = bias; c.p.act = act;
+  c.p.out[0] = out; c.p.ldo[0] = ldo; c.p.out_bf16 = out_bf16 ? 1 : 0;
+  c.p.skip = skip;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// other launch helpers
+// ------------------------------------------------------------------------------------------------
+static int launch_ln(gitb200_engine* h, const LnParams& p, int D, cudaStream_t st) {
+  const int grid = (p.rows + 7) / 8;
+  if (D == 768) layernorm_kernel<768><<<grid, 256, 0, st>>>(p);
+  else if (D == 1024) layernorm_kernel<1024><<<grid, 256, 0, st>>>(p);
+  else return fail(h, "layernorm: unsupported width %d", D);
+  CKL(h, "layernorm_kernel");
+  return 0;
+}
+static LnParams ln_params(const float* x, const float* bias, const float* resid, const float* g, const float* b,
+                          float eps, float* of32, bf16* obf16, int rows) {
+  LnParams p{};
+  p.x = x; p.bias = bias; p.resid = resid; p.gamma = g; p.beta = b; p.eps = eps;
+  p.out_f32 = of32; p.out_bf16 = obf16; p.rows = rows;
+  return p;
+}
+
+static int launch_attention(gitb200_engine* h, const AttnParams& ap, cudaStream_t st) {
+  AttnParams p = ap;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  dim3 grid((p.S + 63) / 64, p.H, p.B);
+  flash_attn_kernel<4><<<grid, 128, 0, st>>>(p);
+  CKL(h, "flash_attn_kernel");
+  return 0;
+}
+
+__global__ void cvt_rows_kernel(const float* __restrict__ src, long long src_ld, bf16* __restrict__ dst, long long dst_ld,
+                                long long rows, long long cols, long long dst_cols) {
+  const long long total = rows * dst_cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / dst_cols, c = i - r * dst_cols;
+    dst[r * dst_ld + c] = __float2bfloat16_rn(c < cols ? src[r * src_ld + c] : 0.0f);
+  }
+}
+__global__ void set_state_kernel(StepState* st, int pos, int cur_len) {
+  st->pos = pos; st->cur_len = cur_len; st->finished = 0; st->final_len = cur_len; st->step = 0;
+  st->empty_caption = 0; st->ticket = 0; st->not_eos = 0;
+}
+__global__ void init_generate_kernel(long long* tokens_out, long long* next_token, float* logprob_sum,
+                                     const long long* prefix, int P, int rows, int max_steps, int sos) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  for (int i = 0; i < P; ++i) tokens_out[static_cast<long long>(r) * max_steps + i] = prefix ? prefix[i] : sos;
+  next_token[r] = prefix ? prefix[0] : sos;
+  logprob_sum[r] = 0.f;
+}
+__global__ void advance_prefix_kernel(StepState* st, long long* next_token, const long long* prefix, int idx, int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) next_token[r] = prefix[idx];
+  if (r == 0) st->pos = st->pos + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy / weights
+// ------------------------------------------------------------------------------------------------
+extern "C" int gitb200_abi_version(void) { return GITB200_ABI_VERSION; }
+
+extern "C" const char* gitb200_last_error(const gitb200_engine* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int64_t gitb200_launch_count(const gitb200_engine* h) { return h ? h->launches : 0; }
+
+extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value) {
+  if (!h || !name) return 1;
+  if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
+  return fail(h, "unknown option %s", name);
+}
+
+extern "C" int gitb200_create(const gitb200_config* cfg, int device, gitb200_engine** out) {
+  gitb200_engine* h = nullptr;
+  if (!cfg || !out) return fail(nullptr, "gitb200_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, "gitb200_create: no CUDA device visible (this engine has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(nullptr, "gitb200_create: bad device %d", device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, "gitb200_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  if (cfg->image_size % cfg->patch != 0) return fail(nullptr, "image_size %% patch != 0");
+  if (cfg->enc_width != 768 && cfg->enc_width != 1024) return fail(nullptr, "enc_width must be 768 or 1024");
+  if (cfg->dec_hidden != 768 || cfg->dec_heads * 64 != cfg->dec_hidden || cfg->enc_heads * 64 != cfg->enc_width)
+    return fail(nullptr, "head dim must be 64 and dec_hidden 768");
+  if (cfg->dec_ffn % 64 != 0) return fail(nullptr, "dec_ffn must be a multiple of 64");
+  h = new gitb200_engine();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->g = cfg->image_size / cfg->patch;
+  h->L = h->g * h->g + 1;
+  h->Kpatch = 3 * cfg->patch * cfg->patch;
+  h->Kp = (h->Kpatch + 63) / 64 * 64;
+  h->d = cfg->enc_width;
+  h->D = cfg->dec_hidden;
+  h->F = cfg->dec_ffn;
+  h->V = cfg->vocab;
+  h->enc.resize(cfg->enc_layers);
+  h->dec.resize(cfg->dec_layers);
+  cudaSetDevice(device);
+  *out = h;
+  return 0;
+}
+
+static void release_all(gitb200_engine* h) {
+  DevBuf* bufs[] = {&h->w_patch, &h->cls, &h->pos_emb, &h->lnpre_g, &h->lnpre_b, &h->lnpost_g, &h->lnpost_b, &h->w_vp,
+                    &h->b_vp, &h->lnvp_g, &h->lnvp_b, &h->words_f32, &h->words_bf16, &h->positions, &h->lnemb_g,
+                    &h->lnemb_b, &h->out_bias, &h->temb, &h->x, &h->h, &h->qkv, &h->ctx, &h->u, &h->feats, &h->feats_f32,
+                    &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->txt_kv, &h->src_row[0],
+                    &h->src_row[1], &h->xd_t, &h->hd_t, &h->qkv_t, &h->ctx_t, &h->t_t, &h->u_t, &h->logits, &h->state,
+                    &h->next_token, &h->logprob_sum, &h->tokens_i64, &h->stage_img, &h->stage_tok, &h->stage_lp,
+                    &h->prefix_dev, &h->beam_ws};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& l : h->enc) {
+    DevBuf* lb[] = {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.ln2g, &l.ln2b, &l.w1, &l.b1, &l.w2, &l.b2};
+    for (DevBuf* b : lb) b->release();
+  }
+  for (auto& l : h->dec) {
+    DevBuf* lb[] = {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.lnag, &l.lnab, &l.w1, &l.b1, &l.w2, &l.b2, &l.lnog, &l.lnob};
+    for (DevBuf* b : lb) b->release();
+  }
+}
+
+extern "C" void gitb200_destroy(gitb200_engine* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  release_all(h);
+  delete h;
+}
+
+// Copy an fp32 source tensor into an engine buffer: fp32 (as is) or bf16 [rows, dst_cols] with zero padding,
+// at a row offset inside the destination (used to fuse q/k/v into one matrix).
+static int store_f32(gitb200_engine* h, DevBuf& dst, size_t total_elems, size_t elem_off, const float* src, size_t n,
+                     cudaStream_t st) {
+  CK(dst.ensure(total_elems * sizeof(float)));
+  CK(cudaMemcpyAsync(dst.as<float>() + elem_off, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+static int store_bf16(gitb200_engine* h, DevBuf& dst, long long total_rows, long long dst_cols, long long row_off,
+                      const float* src, long long rows, long long cols, cudaStream_t st) {
+  const bool fresh = dst.p == nullptr;
+  CK(dst.ensure(static_cast<size_t>(total_rows) * dst_cols * sizeof(bf16)));
+  (void)fresh;
+  const long long total = rows * dst_cols;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  cvt_rows_kernel<<<grid, 256, 0, st>>>(src, cols, dst.as<bf16>() + row_off * dst_cols, dst_cols, rows, cols, dst_cols);
+  CKL(h, "cvt_rows_kernel");
+  return 0;
+}
+
+static bool shape_is(const int64_t* s, int nd, std::initializer_list<int64_t> want) {
+  if (nd != static_cast<int>(want.size())) return false;
+  int i = 0;
+  for (int64_t w : want) if (s[i++] != w) return false;
+  return true;
+}
+
+extern "C" int gitb200_set_weight(gitb200_engine* h, const char* ref_key, const void* dev_ptr, const int64_t* shape,
+                                  int ndim, int dtype, void* stream) {
+  if (!h) return 1;
+  if (!ref_key || !dev_ptr || !shape) return fail(h, "set_weight: null argument");
+  if (dtype != GITB200_F32) return fail(h, "set_weight(%s): only fp32 sources are accepted", ref_key);
+  cudaSetDevice(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* src = static_cast<const float*>(dev_ptr);
+  const std::string key(ref_key);
+  const int d = h->d, D = h->D, F = h->F, V = h->V, L = h->L;
+  auto bad_shape = [&]() { return fail(h, "set_weight(%s): unexpected shape", ref_key); };
+  h->finalized = false;
+  int layer = -1;
+  char sub[128];
+  if (key == "image_encoder.proj" || key == "textual.output.weight") { h->seen.insert(key); return 0; }
+  if (key == "image_encoder.class_embedding") {
+    if (!shape_is(shape, ndim, {d})) return bad_shape();
+    TRY(store_f32(h, h->cls, d, 0, src, d, st));
+  } else if (key == "image_encoder.positional_embedding") {
+    if (!shape_is(shape, ndim, {L, d})) return bad_shape();
+    TRY(store_f32(h, h->pos_emb, static_cast<size_t>(L) * d, 0, src, static_cast<size_t>(L) * d, st));
+  } else if (key == "image_encoder.conv1.weight") {
+    if (!shape_is(shape, ndim, {d, 3, h->cfg.patch, h->cfg.patch})) return bad_shape();
+    TRY(store_bf16(h, h->w_patch, d, h->Kp, 0, src, d, h->Kpatch, st));
+  } else if (key == "image_encoder.ln_pre.weight") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, h->lnpre_g, d, 0, src, d, st));
+  } else if (key == "image_encoder.ln_pre.bias") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, h->lnpre_b, d, 0, src, d, st));
+  } else if (key == "image_encoder.ln_post.weight") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, h->lnpost_g, d, 0, src, d, st));
+  } else if (key == "image_encoder.ln_post.bias") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, h->lnpost_b, d, 0, src, d, st));
+  } else if (sscanf(ref_key, "image_encoder.transformer.resblocks.%d.%127s", &layer, sub) == 2) {
+    if (layer < 0 || layer >= static_cast<int>(h->enc.size())) return fail(h, "set_weight(%s): layer out of range", ref_key);
+    EncLayer& l = h->enc[layer];
+    const std::string s(sub);
+    if (s == "attn.in_proj_weight") { if (!shape_is(shape, ndim, {3 * d, d})) return bad_shape(); TRY(store_bf16(h, l.wqkv, 3 * d, d, 0, src, 3 * d, d, st)); }
+    else if (s == "attn.in_proj_bias") { if (!shape_is(shape, ndim, {3 * d})) return bad_shape(); TRY(store_f32(h, l.bqkv, 3 * d, 0, src, 3 * d, st)); }
+    else if (s == "attn.out_proj.weight") { if (!shape_is(shape, ndim, {d, d})) return bad_shape(); TRY(store_bf16(h, l.wo, d, d, 0, src, d, d, st)); }
+    else if (s == "attn.out_proj.bias") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, l.bo, d, 0, src, d, st)); }
+    else if (s == "ln_1.weight") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, l.ln1g, d, 0, src, d, st)); }
+    else if (s == "ln_1.bias") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, l.ln1b, d, 0, src, d, st)); }
+    else if (s == "ln_2.weight") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, l.ln2g, d, 0, src, d, st)); }
+    else if (s == "ln_2.bias") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, l.ln2b, d, 0, src, d, st)); }
+    else if (s == "mlp.c_fc.weight") { if (!shape_is(shape, ndim, {4 * d, d})) return bad_shape(); TRY(store_bf16(h, l.w1, 4 * d, d, 0, src, 4 * d, d, st)); }
+    else if (s == "mlp.c_fc.bias") { if (!shape_is(shape, ndim, {4 * d})) return bad_shape(); TRY(store_f32(h, l.b1, 4 * d, 0, src, 4 * d, st)); }
+    else if (s == "mlp.c_proj.weight") { if (!shape_is(shape, ndim, {d, 4 * d})) return bad_shape(); TRY(store_bf16(h, l.w2, d, 4 * d, 0, src, d, 4 * d, st)); }
+    else if (s == "mlp.c_proj.bias") { if (!shape_is(shape, ndim, {d})) return bad_shape(); TRY(store_f32(h, l.b2, d, 0, src, d, st)); }
+    else return fail(h, "set_weight: unknown key %s", ref_key);
+  } else if (key == "textual.visual_projection.0.weight") {
+    if (!shape_is(shape, ndim, {D, d})) return bad_shape();
+    TRY(store_bf16(h, h->w_vp, D, d, 0, src, D, d, st));
+  } else if (key == "textual.visual_projection.0.bias") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, h->b_vp, D, 0, src, D, st));
+  } else if (key == "textual.visual_projection.1.weight") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, h->lnvp_g, D, 0, src, D, st));
+  } else if (key == "textual.visual_projection.1.bias") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, h->lnvp_b, D, 0, src, D, st));
+  } else if (key == "textual.embedding.words.weight") {
+    if (!shape_is(shape, ndim, {V, D})) return bad_shape();
+    TRY(store_f32(h, h->words_f32, static_cast<size_t>(V) * D, 0, src, static_cast<size_t>(V) * D, st));
+    TRY(store_bf16(h, h->words_bf16, V, D, 0, src, V, D, st));
+  } else if (key == "textual.embedding.positions.weight") {
+    if (!shape_is(shape, ndim, {h->cfg.max_positions, D})) return bad_shape();
+    TRY(store_f32(h, h->positions, static_cast<size_t>(h->cfg.max_positions) * D, 0, src, static_cast<size_t>(h->cfg.max_positions) * D, st));
+  } else if (key == "textual.embedding.layer_norm.weight") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, h->lnemb_g, D, 0, src, D, st));
+  } else if (key == "textual.embedding.layer_norm.bias") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, h->lnemb_b, D, 0, src, D, st));
+  } else if (key == "textual.output.bias") { if (!shape_is(shape, ndim, {V})) return bad_shape(); TRY(store_f32(h, h->out_bias, V, 0, src, V, st));
+  } else if (sscanf(ref_key, "textual.transformer.encoder.layer.%d.%127s", &layer, sub) == 2) {
+    if (layer < 0 || layer >= static_cast<int>(h->dec.size())) return fail(h, "set_weight(%s): layer out of range", ref_key);
+    DecLayer& l = h->dec[layer];
+    const std::string s(sub);
+    const char* qkvn[3] = {"query", "key", "value"};
+    bool done = false;
+    for (int i = 0; i < 3 && !done; ++i) {
+      if (s == std::string("attention.self.") + qkvn[i] + ".weight") {
+        if (!shape_is(shape, ndim, {D, D})) return bad_shape();
+        TRY(store_bf16(h, l.wqkv, 3 * D, D, static_cast<long long>(i) * D, src, D, D, st));
+        done = true;
+      } else if (s == std::string("attention.self.") + qkvn[i] + ".bias") {
+        if (!shape_is(shape, ndim, {D})) return bad_shape();
+        TRY(store_f32(h, l.bqkv, 3 * D, static_cast<size_t>(i) * D, src, D, st));
+        done = true;
+      }
+    }
+    if (done) { /* stored */ }
+    else if (s == "attention.output.dense.weight") { if (!shape_is(shape, ndim, {D, D})) return bad_shape(); TRY(store_bf16(h, l.wo, D, D, 0, src, D, D, st)); }
+    else if (s == "attention.output.dense.bias") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, l.bo, D, 0, src, D, st)); }
+    else if (s == "attention.output.LayerNorm.weight") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, l.lnag, D, 0, src, D, st)); }
+    else if (s == "attention.output.LayerNorm.bias") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, l.lnab, D, 0, src, D, st)); }
+    else if (s == "intermediate.dense.weight") { if (!shape_is(shape, ndim, {F, D})) return bad_shape(); TRY(store_bf16(h, l.w1, F, D, 0, src, F, D, st)); }
+    else if (s == "intermediate.dense.bias") { if (!shape_is(shape, ndim, {F})) return bad_shape(); TRY(store_f32(h, l.b1, F, 0, src, F, st)); }
+    else if (s == "output.dense.weight") { if (!shape_is(shape, ndim, {D, F})) return bad_shape(); TRY(store_bf16(h, l.w2, D, F, 0, src, D, F, st)); }
+    else if (s == "output.dense.bias") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, l.b2, D, 0, src, D, st)); }
+    else if (s == "output.LayerNorm.weight") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, l.lnog, D, 0, src, D, st)); }
+    else if (s == "output.LayerNorm.bias") { if (!shape_is(shape, ndim, {D})) return bad_shape(); TRY(store_f32(h, l.lnob, D, 0, src, D, st)); }
+    else return fail(h, "set_weight: unknown key %s", ref_key);
+  } else if (sscanf(ref_key, "img_temperal_embedding.%d", &layer) == 1) {
+    if (layer < 0 || layer >= h->cfg.num_frames_emb) return fail(h, "set_weight(%s): frame out of range", ref_key);
+    if (!shape_is(shape, ndim, {1, 1, d})) return bad_shape();
+    TRY(store_f32(h, h->temb, static_cast<size_t>(h->cfg.num_frames_emb) * d, static_cast<size_t>(layer) * d, src, d, st));
+  } else {
+    return fail(h, "set_weight: unknown key %s", ref_key);
+  }
+  h->seen.insert(key);
+  return 0;
+}
+
+extern "C" int gitb200_finalize_weights(gitb200_engine* h, void* stream) {
+  if (!h) return 1;
+  cudaSetDevice(h->device);
+  std::vector<std::string> need = {"image_encoder.class_embedding", "image_encoder.positional_embedding",
+                                   "image_encoder.conv1.weight", "image_encoder.ln_pre.weight", "image_encoder.ln_pre.bias",
+                                   "image_encoder.ln_post.weight", "image_encoder.ln_post.bias",
+                                   "textual.visual_projection.0.weight", "textual.visual_projection.0.bias",
+                                   "textual.visual_projection.1.weight", "textual.visual_projection.1.bias",
+                                   "textual.embedding.words.weight", "textual.embedding.positions.weight",
+                                   "textual.embedding.layer_norm.weight", "textual.embedding.layer_norm.bias",
+                                   "textual.output.bias"};
+  const char* encs[] = {"attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
+                        "ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias",
+                        "mlp.c_proj.weight", "mlp.c_proj.bias"};
+  for (int i = 0; i < h->cfg.enc_layers; ++i)
+    for (const char* s : encs) need.push_back("image_encoder.transformer.resblocks." + std::to_string(i) + "." + s);
+  const char* decs[] = {"attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight",
+                        "attention.self.key.bias", "attention.self.value.weight", "attention.self.value.bias",
+                        "attention.output.dense.weight", "attention.output.dense.bias", "attention.output.LayerNorm.weight",
+                        "attention.output.LayerNorm.bias", "intermediate.dense.weight", "intermediate.dense.bias",
+                        "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"};
+  for (int j = 0; j < h->cfg.dec_layers; ++j)
+    for (const char* s : decs) need.push_back("textual.transformer.encoder.layer." + std::to_string(j) + "." + s);
+  for (int f = 0; f < h->cfg.num_frames_emb; ++f) need.push_back("img_temperal_embedding." + std::to_string(f));
+  for (const std::string& k : need)
+    if (!h->seen.count(k)) return fail(h, "finalize_weights: missing tensor %s", k.c_str());
+  CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  CK(cudaGetLastError());
+  h->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hot path A: encoder
+// ------------------------------------------------------------------------------------------------
+static int encode_impl(gitb200_engine* h, const float* images, int B, int frames, bool list_input, float* feats_out,
+                       cudaStream_t st) {
+  if (!h->finalized) return fail(h, "weights not finalized");
+  if (B < 1 || frames < 1) return fail(h, "encode: bad batch/frames");
+  if (list_input && h->cfg.num_frames_emb > 0 && frames > h->cfg.num_frames_emb) {
+    // reference zip() truncates to the number of temporal embeddings (layers/decoder.py:848-849)
+    frames = h->cfg.num_frames_emb;
+  }
+  const int d = h->d, L = h->L, g = h->g, Kp = h->Kp, H = h->cfg.enc_heads;
+  const int NI = B * frames;
+  const long long Me = static_cast<long long>(NI) * L;
+  CK(h->x.ensure(Me * d * 4));
+  CK(h->h.ensure(Me * d * 2));
+  CK(h->qkv.ensure(Me * 3 * d * 2));
+  CK(h->ctx.ensure(Me * d * 2));
+  CK(h->u.ensure(std::max<long long>(Me * 4 * d * 2, static_cast<long long>(NI) * g * g * Kp * 2)));
+  CK(h->feats.ensure(Me * d * 2));
+  float* x = h->x.as<float>();
+  bf16* hb = h->h.as<bf16>();
+  bf16* qkv = h->qkv.as<bf16>();
+  bf16* ctx = h->ctx.as<bf16>();
+  bf16* u = h->u.as<bf16>();
+
+  // patch embedding: im2col + GEMM, rows land at token index 1 + patch (CLS row is filled by the next kernel)
+  {
+    const long long total = static_cast<long long>(NI) * g * g * (Kp / 8);
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 16));
+    im2col_patch_kernel<<<grid, 256, 0, st>>>(images, u, NI, h->cfg.image_size, h->cfg.patch, g, Kp);
+    CKL(h, "im2col_patch_kernel");
+    GemmCall c = gemm_plain(u, Kp, h->w_patch.as<bf16>(), Kp, NI * g * g, d, Kp, nullptr, ACT_NONE, nullptr, x, false);
+    c.p.rows_per_batch = g * g;
+    c.p.batch_stride[0] = L;
+    c.p.row_offset = 1;
+    TRY(launch_gemm(h, c, st));
+    const int gridr = static_cast<int>((Me + 7) / 8);
+    if (d == 768)
+      cls_pos_lnpre_kernel<768><<<gridr, 256, 0, st>>>(x, h->cls.as<float>(), h->pos_emb.as<float>(), h->lnpre_g.as<float>(), h->lnpre_b.as<float>(), static_cast<int>(Me), L);
+    else
+      cls_pos_lnpre_kernel<1024><<<gridr, 256, 0, st>>>(x, h->cls.as<float>(), h->pos_emb.as<float>(), h->lnpre_g.as<float>(), h->lnpre_b.as<float>(), static_cast<int>(Me), L);
+    CKL(h, "cls_pos_lnpre_kernel");
+  }
+  for (int i = 0; i < h->cfg.enc_layers; ++i) {
+    EncLayer& l = h->enc[i];
+    TRY(launch_ln(h, ln_params(x, nullptr, nullptr, l.ln1g.as<float>(), l.ln1b.as<float>(), 1e-5f, nullptr, hb, static_cast<int>(Me)), d, st));
+    TRY(launch_gemm(h, gemm_plain(hb, d, l.wqkv.as<bf16>(), d, static_cast<int>(Me), 3 * d, d, l.bqkv.as<float>(), ACT_NONE, nullptr, qkv, true), st));
+    AttnParams ap{};
+    ap.q = qkv; ap.k = qkv + d; ap.v = qkv + 2 * d; ap.out = ctx;
+    ap.B = NI; ap.S = L; ap.H = H;
+    ap.q_rs = 3 * d; ap.kv_rs = 3 * d; ap.q_bs = static_cast<long long>(L) * 3 * d; ap.kv_bs = ap.q_bs;
+    ap.o_rs = d; ap.o_bs = static_cast<long long>(L) * d;
+    TRY(launch_attention(h, ap, st));
+    TRY(launch_gemm(h, gemm_plain(ctx, d, l.wo.as<bf16>(), d, static_cast<int>(Me), d, d, l.bo.as<float>(), ACT_NONE, x, x, false), st));
+    TRY(launch_ln(h, ln_params(x, nullptr, nullptr, l.ln2g.as<float>(), l.ln2b.as<float>(), 1e-5f, nullptr, hb, static_cast<int>(Me)), d, st));
+    TRY(launch_gemm(h, gemm_plain(hb, d, l.w1.as<bf16>(), d, static_cast<int>(Me), 4 * d, d, l.b1.as<float>(), ACT_QUICKGELU, nullptr, u, true), st));
+    TRY(launch_gemm(h, gemm_plain(u, 4 * d, l.w2.as<bf16>(), 4 * d, static_cast<int>(Me), d, 4 * d, l.b2.as<float>(), ACT_NONE, x, x, false), st));
+  }
+  // ln_post on all tokens (+ temporal embedding), re-ordered to [B, frames*L, d]
+  {
+    LnParams p = ln_params(x, nullptr, nullptr, h->lnpost_g.as<float>(), h->lnpost_b.as<float>(), 1e-5f, feats_out, h->feats.as<bf16>(), static_cast<int>(Me));
+    p.remap_B = B; p.remap_F = frames; p.remap_L = L;
+    // temporal embeddings only for list inputs (reference layers/decoder.py:846-849; a bare tensor skips them)
+    p.temb = (list_input && h->cfg.num_frames_emb > 0) ? h->temb.as<float>() : nullptr;
+    TRY(launch_ln(h, p, d, st));
+  }
+  h->cur_B = B;
+  h->cur_frames = frames;
+  h->cur_M = frames * L;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hot path B: prefill (image rows of the decoder, computed once) + decode step
+// ------------------------------------------------------------------------------------------------
+static bf16* img_kv_ptr(gitb200_engine* h, int layer, int kv) {
+  const long long per = static_cast<long long>(h->cur_B) * h->cur_M * h->D;
+  return h->img_kv.as<bf16>() + (static_cast<long long>(layer) * 2 + kv) * per;
+}
+static bf16* txt_kv_ptr(gitb200_engine* h, int layer, int kv) {
+  const long long per = static_cast<long long>(h->cur_rows) * h->T_alloc * h->D;
+  return h->txt_kv.as<bf16>() + (static_cast<long long>(layer) * 2 + kv) * per;
+}
+
+static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* vproj_out, cudaStream_t st) {
+  if (B != h->cur_B || h->cur_M <= 0) return fail(h, "prefill: call encode with the same batch first");
+  const int D = h->D, F = h->F, d = h->d, M = h->cur_M, nl = h->cfg.dec_layers, H = h->cfg.dec_heads;
+  const long long rows = static_cast<long long>(B) * M;
+  const int R = B * beam;
+  CK(h->pt.ensure(rows * D * 4));
+  CK(h->pxd.ensure(rows * D * 4));
+  CK(h->phd.ensure(rows * D * 2));
+  CK(h->pq.ensure(rows * D * 2));
+  CK(h->pctx.ensure(rows * D * 2));
+  CK(h->pu.ensure(rows * F * 2));
+  CK(h->img_kv.ensure(static_cast<long long>(nl) * 2 * rows * D * 2));
+  CK(h->txt_kv.ensure(static_cast<long long>(nl) * 2 * R * T_alloc * D * 2));
+  CK(h->src_row[0].ensure(static_cast<size_t>(R) * T_alloc * 4));
+  CK(h->src_row[1].ensure(static_cast<size_t>(R) * T_alloc * 4));
+  CK(h->xd_t.ensure(static_cast<size_t>(R) * D * 4));
+  CK(h->hd_t.ensure(static_cast<size_t>(R) * D * 2));
+  CK(h->qkv_t.ensure(static_cast<size_t>(R) * 3 * D * 4));
+  CK(h->ctx_t.ensure(static_cast<size_t>(R) * D * 2));
+  CK(h->t_t.ensure(static_cast<size_t>(R) * D * 4));
+  CK(h->u_t.ensure(static_cast<size_t>(R) * F * 2));
+  CK(h->logits.ensure(static_cast<size_t>(R) * h->V * 4));
+  CK(h->state.ensure(sizeof(StepState)));
+  CK(h->next_token.ensure(static_cast<size_t>(R) * 8));
+  CK(h->logprob_sum.ensure(static_cast<size_t>(R) * 4));
+  h->cur_beam = beam;
+  h->cur_rows = R;
+  h->T_alloc = T_alloc;
+  float* t = h->pt.as<float>();
+  float* xd = h->pxd.as<float>();
+  bf16* hd = h->phd.as<bf16>();
+  bf16* q = h->pq.as<bf16>();
+  bf16* ctx = h->pctx.as<bf16>();
+  bf16* u = h->pu.as<bf16>();
+  // split-K accumulation buffer of the decode step must start at zero
+  CK(cudaMemsetAsync(h->t_t.p, 0, static_cast<size_t>(R) * D * 4, st));
+
+  // visual projection: Linear(dv -> 768) + LayerNorm(1e-5)
+  TRY(launch_gemm(h, gemm_plain(h->feats.as<bf16>(), d, h->w_vp.as<bf16>(), d, static_cast<int>(rows), D, d, h->b_vp.as<float>(), ACT_NONE, nullptr, t, false), st));
+  {
+    LnParams p = ln_params(t, nullptr, nullptr, h->lnvp_g.as<float>(), h->lnvp_b.as<float>(), 1e-5f, xd, hd, static_cast<int>(rows));
+    TRY(launch_ln(h, p, D, st));
+    if (vproj_out) CK(cudaMemcpyAsync(vproj_out, xd, rows * D * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  for (int j = 0; j < nl; ++j) {
+    DecLayer& l = h->dec[j];
+    // fused q|k|v projection; k and v rows go straight into the image K/V cache
+    GemmCall c = gemm_plain(hd, D, l.wqkv.as<bf16>(), D, static_cast<int>(rows), 3 * D, D, l.bqkv.as<float>(), ACT_NONE, nullptr, q, true);
+    c.p.seg_n = D;
+    c.p.out[0] = q; c.p.out[1] = img_kv_ptr(h, j, 0); c.p.out[2] = img_kv_ptr(h, j, 1);
+    c.p.ldo[0] = c.p.ldo[1] = c.p.ldo[2] = D;
+    TRY(launch_gemm(h, c, st));
+    if (j + 1 == nl) break;  // image rows of the last layer are never read (text rows only need their K/V)
+    AttnParams ap{};
+    ap.q = q; ap.k = img_kv_ptr(h, j, 0); ap.v = img_kv_ptr(h, j, 1); ap.out = ctx;
+    ap.B = B; ap.S = M; ap.H = H;
+    ap.q_rs = D; ap.kv_rs = D; ap.q_bs = static_cast<long long>(M) * D; ap.kv_bs = ap.q_bs; ap.o_rs = D; ap.o_bs = ap.q_bs;
+    TRY(launch_attention(h, ap, st));
+    TRY(launch_gemm(h, gemm_plain(ctx, D, l.wo.as<bf16>(), D, static_cast<int>(rows), D, D, l.bo.as<float>(), ACT_NONE, xd, t, false), st));
+    TRY(launch_ln(h, ln_params(t, nullptr, nullptr, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, static_cast<int>(rows)), D, st));
+    TRY(launch_gemm(h, gemm_plain(hd, D, l.w1.as<bf16>(), D, static_cast<int>(rows), F, D, l.b1.as<float>(), ACT_GELU_ERF, nullptr, u, true), st));
+    TRY(launch_gemm(h, gemm_plain(u, F, l.w2.as<bf16>(), F, static_cast<int>(rows), D, F, l.b2.as<float>(), ACT_NONE, xd, t, false), st));
+    TRY(launch_ln(h, ln_params(t, nullptr, nullptr, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, static_cast<int>(rows)), D, st));
+  }
+  return 0;
+}
+
+// One decode step for the `rows` sequences: embed next_token at state->pos, 6 layers against the KV caches,
+// optional LM head -> h->logits.  Every kernel reads the position / finished flag from device state so the
+// same launch sequence (and CUDA graph) serves every step.
+static int step_layers(gitb200_engine* h, const long long* tokens, const int* src_row, bool lm_head, cudaStream_t st) {
+  const int D = h->D, F = h->F, R = h->cur_rows, nl = h->cfg.dec_layers, beam = h->cur_beam;
+  StepState* state = h->state.as<StepState>();
+  const int* skip = &state->finished;
+  float* xd = h->xd_t.as<float>();
+  bf16* hd = h->hd_t.as<bf16>();
+  float* qkv = h->qkv_t.as<float>();
+  bf16* ctx = h->ctx_t.as<bf16>();
+  float* t = h->t_t.as<float>();
+  bf16* u = h->u_t.as<bf16>();
+  embed_ln_kernel<768><<<(R + 7) / 8, 256, 0, st>>>(tokens, 1, h->words_f32.as<float>(), h->positions.as<float>(),
+                                                   h->lnemb_g.as<float>(), h->lnemb_b.as<float>(), xd, hd, R, 0, state, h->V);
+  CKL(h, "embed_ln_kernel");
+  const size_t attn_smem = static_cast<size_t>(beam) * (h->cur_M + h->T_alloc) * sizeof(float);
+  for (int j = 0; j < nl; ++j) {
+    DecLayer& l = h->dec[j];
+    TRY(launch_gemm(h, gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, l.bqkv.as<float>(), ACT_NONE, qkv, 3 * D, false, 1, skip), st));
+    DecAttnParams ap{};
+    ap.qkv = qkv; ap.img_k = img_kv_ptr(h, j, 0); ap.img_v = img_kv_ptr(h, j, 1);
+    ap.txt_k = txt_kv_ptr(h, j, 0); ap.txt_v = txt_kv_ptr(h, j, 1);
+    ap.src_row = src_row; ap.ctx = ctx; ap.B = h->cur_B; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
+    ap.state = state;
+    dim3 grid(h->cfg.dec_heads, h->cur_B);
+    if (beam == 1) decode_attn_kernel<1><<<grid, 128, attn_smem, st>>>(ap);
+    else if (beam == 4) decode_attn_kernel<4><<<grid, 128, attn_smem, st>>>(ap);
+    else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
+    CKL(h, "decode_attn_kernel");
+    TRY(launch_gemm(h, gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 2, skip), st));
+    {
+      LnParams p = ln_params(t, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, R);
+      p.zero_x = 1; p.skip_flag = skip;
+      TRY(launch_ln(h, p, D, st));
+    }
+    TRY(launch_gemm(h, gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip), st));
+    TRY(launch_gemm(h, gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, 4, skip), st));
+    {
+      LnParams p = ln_params(t, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, R);
+      p.zero_x = 1; p.skip_flag = skip;
+      TRY(launch_ln(h, p, D, st));
+    }
+  }
+  if (lm_head)
+    TRY(launch_gemm(h, gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, h->logits.p, h->V, false, 1, skip), st));
+  return 0;
+}
+
+static int set_attn_smem_limit(gitb200_engine* h) {
+  const size_t need = static_cast<size_t>(h->cur_beam) * (h->cur_M + h->T_alloc) * sizeof(float);
+  if (need > 200 * 1024) return fail(h, "decode attention: sequence too long for the score buffer (%zu bytes)", need);
+  if (need > 40 * 1024) {
+    CK(cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need)));
+    CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need)));
+  }
+  return 0;
+}
+
+#include "engine_api.inc"

@@ -1,0 +1,379 @@
+// Row-wise HBM-bound kernels of the GIT hot path: LayerNorm (+bias/+residual/+temporal embedding),
+// patch im2col, CLS/pos-embed/ln_pre, token embedding + LN, and the greedy selection kernels.
+// One warp per row, 128-bit loads/stores, fp32 statistics (two-pass: mean, then biased variance,
+// like torch.nn.functional.layer_norm).
+#pragma once
+#include "ptx.cuh"
+
+namespace gitb200 {
+
+// Decode-loop state shared by the kernels of one generate() call (device memory, one per engine).
+struct StepState {
+  int pos;            // text position of the token fed at the current step (0-based, prefix included)
+  int cur_len;        // tokens currently in tokens_out (start tokens + generated)
+  int finished;       // greedy: every row ended with EOS -> remaining steps are no-ops
+  int final_len;      // number of valid columns of tokens_out
+  int step;           // number of decode steps executed so far
+  int empty_caption;  // greedy step-0 special case (reference layers/decoder.py:279-291)
+  unsigned int ticket;
+  int not_eos;        // rows whose newest token is not EOS (per step, reset by the last block)
+};
+
+struct LnParams {
+  const float* x;        // [rows, D] fp32 (ldx == D)
+  const float* bias;     // [D] or null: added to x first
+  const float* resid;    // [rows, D] or null: added to x first
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* out_f32;        // may alias x (in place) or be null
+  __nv_bfloat16* out_bf16;  // or null
+  int rows;
+  int zero_x;            // write zeros back to x after reading (split-K accumulation buffers)
+  // optional frame remap (video path, reference layers/decoder.py:846-851): input row (f*B + b)*L + l ->
+  // output row b*(F*L) + f*L + l, plus `+ temb[f]` AFTER the normalisation.
+  const float* temb;     // [F, D] or null
+  int remap_B, remap_F, remap_L;  // remap_F == 0 -> identity
+  const int* skip_flag;  // device int: non-zero -> kernel is a no-op (finished decode)
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  static_assert(D % 128 == 0, "D");
+  constexpr int NV = D / 128;
+  if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 v[NV];
+  const float4* xp = reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xp[i * 32 + lane];
+  if (p.zero_x) {
+    float4* zp = reinterpret_cast<float4*>(const_cast<float*>(p.x) + static_cast<long long>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) zp[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (p.bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 b = __ldg(bp + i * 32 + lane);
+      v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+    }
+  }
+  if (p.resid != nullptr) {
+    const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 r = rp[i * 32 + lane];
+      v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + p.eps);
+
+  long long orow = row;
+  int frame = 0;
+  if (p.remap_F > 0) {
+    const int img = row / p.remap_L;
+    const int l = row - img * p.remap_L;
+    frame = img / p.remap_B;
+    const int b = img - frame * p.remap_B;
+    orow = (static_cast<long long>(b) * p.remap_F + frame) * p.remap_L + l;
+  }
+  const float4* gp = reinterpret_cast<const float4*>(p.gamma);
+  const float4* bp = reinterpret_cast<const float4*>(p.beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(gp + i * 32 + lane);
+    const float4 b = __ldg(bp + i * 32 + lane);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (p.temb != nullptr) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p.temb + static_cast<long long>(frame) * D) + i * 32 + lane);
+      o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+    }
+    if (p.out_f32 != nullptr) reinterpret_cast<float4*>(p.out_f32 + orow * D)[i * 32 + lane] = o;
+    if (p.out_bf16 != nullptr) {
+      uint2 pk;
+      pk.x = pack_bf16(o.x, o.y);
+      pk.y = pack_bf16(o.z, o.w);
+      reinterpret_cast<uint2*>(p.out_bf16 + orow * D)[i * 32 + lane] = pk;
+    }
+  }
+}
+
+// Patch im2col for the stride==kernel conv (reference layers/CLIP/model.py:224,242):
+// A[(img, py, px)][(c, ky, kx)] = img[c, py*p+ky, px*p+kx], zero-padded to Kp columns, bf16.
+__global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int n_img, int S,
+                                    int p, int g, int Kp) {
+  const long long total = static_cast<long long>(n_img) * g * g * (Kp / 8);
+  const int K = 3 * p * p;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kc = static_cast<int>(idx % (Kp / 8));
+    const long long row = idx / (Kp / 8);
+    const int px = static_cast<int>(row % g);
+    const int py = static_cast<int>((row / g) % g);
+    const long long im = row / (g * g);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kc * 8 + j;
+      float x = 0.f;
+      if (k < K) {
+        const int c = k / (p * p);
+        const int r = k - c * p * p;
+        const int ky = r / p;
+        const int kx = r - ky * p;
+        x = __ldg(img + ((im * 3 + c) * S + (py * p + ky)) * static_cast<long long>(S) + (px * p + kx));
+      }
+      v[j] = x;
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]);
+    o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]);
+    o.w = pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(A + row * Kp)[kc] = o;
+  }
+}
+
+// x[img, l] = ln_pre((l == 0 ? class_embedding : patch_out[img, l]) + positional_embedding[l])
+// in place on the fp32 residual stream (reference layers/CLIP/model.py:254-257).
+template <int D>
+__global__ void __launch_bounds__(256)
+cls_pos_lnpre_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int L) {
+  constexpr int NV = D / 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int l = row % L;
+  float4 v[NV];
+  const float4* src = (l == 0) ? reinterpret_cast<const float4*>(cls)
+                               : reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+  const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<long long>(l) * D);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = src[i * 32 + lane];
+    const float4 b = __ldg(pp + i * 32 + lane);
+    v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + 1e-5f);
+  float4* op = reinterpret_cast<float4*>(x + static_cast<long long>(row) * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    op[i * 32 + lane] = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                    (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+  }
+}
+
+// e = LN(words[tok] + positions[pos], eps 1e-8) (reference layers/decoder.py:65-78); one warp per row.
+// tokens come from `tokens` (int64 [rows], stride tok_stride) ; position = pos_base + (state ? state->pos : 0).
+template <int D>
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const long long* __restrict__ tokens, long long tok_stride, const float* __restrict__ words,
+                const float* __restrict__ positions, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int rows, int pos_base,
+                const StepState* __restrict__ state, int vocab) {
+  constexpr int NV = D / 128;
+  if (state != nullptr && state->finished) return;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  long long tok = tokens[row * tok_stride];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  const int pos = pos_base + (state != nullptr ? state->pos : 0);
+  const float4* wp = reinterpret_cast<const float4*>(words + tok * D);
+  const float4* pp = reinterpret_cast<const float4*>(positions + static_cast<long long>(pos) * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = __ldg(wp + i * 32 + lane);
+    const float4 b = __ldg(pp + i * 32 + lane);
+    v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + 1e-8f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                           (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * D)[i * 32 + lane] = o;
+    uint2 pk;
+    pk.x = pack_bf16(o.x, o.y);
+    pk.y = pack_bf16(o.z, o.w);
+    reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[i * 32 + lane] = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Greedy selection = the body of AutoRegressiveBeamSearch.search for beam 1 / per-node 1
+// (reference layers/decoder.py:258-273 first step, :313-417 loop): no-repeat scatter(-10000) on the
+// input token (not on the first step), EOS forcing, log_softmax, argmax (lowest index on exact ties),
+// logprob accumulation, all-EOS early exit.  One CTA per row.
+// ------------------------------------------------------------------------------------------------
+struct SelectParams {
+  const float* logits;      // [rows, V]
+  int V;
+  int rows;
+  int eos;
+  int prefix_len;           // P
+  int max_steps;
+  long long* tokens_out;    // [rows, max_steps]
+  float* logprob_sum;       // [rows]
+  long long* next_token;    // [rows] input of the next step
+  const long long* forced;  // [rows, max_steps] or null
+  StepState* state;
+  float* step_logits;       // optional dump [steps, rows, V]
+};
+
+__global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p) {
+  StepState* st = p.state;
+  if (st->finished) return;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int step = st->step;
+  const int cur_len = st->cur_len;
+  const float* z = p.logits + static_cast<long long>(row) * p.V;
+  // The input token of this step (== our previous choice unless teacher forcing is on): the reference's
+  // masks are functions of the *input* sequence (predictions_so_far[:, -1]).
+  const long long last = p.next_token[row];
+  const bool first = (step == 0);
+  const bool row_done = (!first) && (last == p.eos);
+  if (p.step_logits != nullptr) {
+    float* dst = p.step_logits + (static_cast<long long>(step) * p.rows + row) * p.V;
+    for (int i = tid; i < p.V; i += blockDim.x) dst[i] = z[i];
+  }
+  __shared__ float s_val[256];
+  __shared__ int s_idx[256];
+  __shared__ float s_sum[256];
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = tid; i < p.V; i += blockDim.x) {
+    float v = z[i];
+    if (!first && i == static_cast<int>(last)) v = -10000.0f;
+    if (v > best) {  // strided scan visits increasing i per thread -> keeps the lowest index on ties
+      best = v;
+      best_i = i;
+    }
+  }
+  s_val[tid] = best;
+  s_idx[tid] = best_i;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const float ov = s_val[tid + o];
+      const int oi = s_idx[tid + o];
+      if (ov > s_val[tid] || (ov == s_val[tid] && oi < s_idx[tid])) {
+        s_val[tid] = ov;
+        s_idx[tid] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  const float mx = s_val[0];
+  const int arg = s_idx[0];
+  float sum = 0.f;
+  for (int i = tid; i < p.V; i += blockDim.x) {
+    float v = z[i];
+    if (!first && i == static_cast<int>(last)) v = -10000.0f;
+    sum += __expf(v - mx);
+  }
+  s_sum[tid] = sum;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) s_sum[tid] += s_sum[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    long long tok;
+    float lp;
+    if (row_done) {  // one-hot EOS distribution: log_softmax gives exactly 0 at EOS
+      tok = p.eos;
+      lp = 0.f;
+    } else {
+      tok = arg;
+      lp = -logf(s_sum[0]);  // z[arg] - mx - log(sum) with z[arg] == mx
+    }
+    p.tokens_out[static_cast<long long>(row) * p.max_steps + cur_len] = tok;
+    p.logprob_sum[row] += lp;
+    long long nxt = tok;
+    if (p.forced != nullptr) nxt = p.forced[static_cast<long long>(row) * p.max_steps + cur_len];
+    p.next_token[row] = nxt;
+    // reference checks `(last_predictions == eos).all()` on the sequence it feeds next
+    if (nxt != p.eos) atomicAdd(&st->not_eos, 1);
+    __threadfence();
+    const unsigned int t = atomicAdd(&st->ticket, 1u);
+    if (t == static_cast<unsigned int>(p.rows) - 1) {  // last row of this step: advance the loop state
+      __threadfence();
+      const int not_eos = atomicAdd(&st->not_eos, 0);
+      st->ticket = 0;
+      st->not_eos = 0;
+      st->cur_len = cur_len + 1;
+      st->final_len = cur_len + 1;
+      st->pos = st->pos + 1;
+      st->step = step + 1;
+      if (not_eos == 0) {
+        st->finished = 1;
+        if (first) st->empty_caption = 1;
+      }
+      if (cur_len + 1 >= p.max_steps) st->finished = 1;
+      __threadfence();
+    }
+  }
+}
+
+// logprobs / num_valid (reference layers/decoder.py:433-438) and EOS padding of the unused tail.
+__global__ void greedy_finalize_kernel(long long* tokens_out, const float* logprob_sum, float* logprobs_out, int rows,
+                                       int max_steps, int prefix_len, int eos, const StepState* st) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int n = st->final_len;
+  int not_eos = 0, has_eos = 0;
+  for (int i = 0; i < n; ++i) {
+    const long long t = tokens_out[static_cast<long long>(row) * max_steps + i];
+    if (t == eos) has_eos = 1; else ++not_eos;
+  }
+  for (int i = n; i < max_steps; ++i) tokens_out[static_cast<long long>(row) * max_steps + i] = eos;
+  int num_valid = not_eos + has_eos - prefix_len;
+  if (num_valid < 1) num_valid = 1;
+  logprobs_out[row] = st->empty_caption ? logprob_sum[row] : logprob_sum[row] / static_cast<float>(num_valid);
+}
+
+}  // namespace gitb200

@@ -1,0 +1,307 @@
+"""Drop-in for the reference's model factory: `get_git_model(tokenizer, param)`
+(reference generativeimage2text/model.py:9-61).
+
+The returned `torch.nn.Module` carries parameters under the reference's own state-dict keys (so
+`torch_common.load_state_dict`, reference torch_common.py:93-145, and `.cuda()/.eval()` work unchanged) and
+its `forward(batch)` accepts the reference's batch dict and returns `{'predictions', 'logprobs'}`
+(reference layers/decoder.py:838-877, 977-1011) -- but no PyTorch op touches the hot path: pixels go in,
+token ids come out of libgitb200.so (hand-written sm_100a kernels).  PyTorch only owns the parameter
+storage, the CUDA stream and the output tensors.
+"""
+import ctypes
+import math
+import warnings
+
+import torch
+from torch import nn
+
+from . import _lib
+from .synthetic import ENCODER_CFG, VOCAB, HIDDEN, DEC_LAYERS, DEC_HEADS, FFN, MAX_POS, state_spec
+
+
+class AutoRegressiveBeamSearch(object):
+    """Search *configuration* mirroring the reference class of the same name (layers/decoder.py:208-222).
+    The engine implements its greedy form (beam_size = per_node_beam_size = 1, the reference's
+    commented-out greedy decoder, model.py:27-33) on the device."""
+
+    def __init__(self, eos_index, max_steps=50, beam_size=5, per_node_beam_size=2, fix_missing_prefix=False):
+        assert fix_missing_prefix, 'should always true'          # reference layers/decoder.py:222
+        self._eos_index = eos_index
+        self.max_steps = max_steps
+        self.beam_size = beam_size
+        self.per_node_beam_size = per_node_beam_size or beam_size
+        self.fix_missing_prefix = fix_missing_prefix
+        if not (self.beam_size == 1 and self.per_node_beam_size == 1):
+            raise NotImplementedError(
+                'AutoRegressiveBeamSearch is implemented for beam_size=1/per_node_beam_size=1 (greedy); '
+                'use GeneratorWithBeamSearch for beam search (the reference default)')
+
+
+class GeneratorWithBeamSearch(object):
+    """Search configuration mirroring reference layers/decoder.py:1056-1081 (the shipped default:
+    beam 4, per-node 2, length_penalty 0.6, model.py:34-40)."""
+
+    def __init__(self, eos_index, max_steps, beam_size, per_node_beam_size=2, length_penalty=1,
+                 repetition_penalty=1, temperature=1):
+        self._eos_index = eos_index
+        self.max_steps = max_steps
+        self.beam_size = beam_size
+        self.per_node_beam_size = per_node_beam_size or beam_size
+        self.length_penalty = length_penalty
+        self.repetition_penalty = repetition_penalty
+        self.temperature = temperature
+        assert self.per_node_beam_size > 1
+        assert self.length_penalty > 0, "`length_penalty` should be strictely positive."
+        assert self.repetition_penalty >= 1.0, "`repetition_penalty` should be >= 1."
+        assert self.temperature > 0, "`temperature` should be strictely positive."
+        if repetition_penalty != 1 or temperature != 1:
+            raise NotImplementedError('repetition_penalty / temperature are not used by get_git_model')
+
+
+class _Holder(nn.Module):
+    """Attribute container so that parameters get the reference's dotted names."""
+
+
+def _set_path(root, dotted, param):
+    parts = dotted.split('.')
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Holder())
+        mod = getattr(mod, p)
+    mod.register_parameter(parts[-1], param)
+
+
+class GitB200CaptioningModel(nn.Module):
+    """Parameter shell + engine handle. See module docstring."""
+
+    def __init__(self, tokenizer, param):
+        super().__init__()
+        self.param = dict(param or {})
+        enc_type = self.param.get('image_encoder_type', 'CLIPViT_B_16')
+        enc = ENCODER_CFG[enc_type]
+        self.image_size = self.param.get('test_crop_size', 224)
+        self.num_image_with_embedding = self.param.get('num_image_with_embedding')
+        self.sos_index = tokenizer.cls_token_id
+        self.eos_index = tokenizer.sep_token_id
+        self.tokenizer = tokenizer
+        if self.param.get('visual_feature_size', 768) != enc['width']:
+            raise ValueError('visual_feature_size must equal the encoder width (grid features are not projected)')
+        words = None
+        for key, shape, (kind, scale) in state_spec(self.param):
+            if kind == 'tied':
+                p = words                                         # reference layers/decoder.py:503-505
+            else:
+                t = torch.empty(shape, dtype=torch.float32)
+                if kind == 'normal':
+                    t.normal_(0.0, scale)
+                elif kind == 'ones':
+                    t.fill_(1.0)
+                else:
+                    t.zero_()
+                p = nn.Parameter(t, requires_grad=False)
+                if key == 'textual.embedding.words.weight':
+                    words = p
+            if key.startswith('img_temperal_embedding.'):
+                continue
+            _set_path(self, key, p)
+        n_emb = self.num_image_with_embedding or 0
+        if n_emb:
+            self.img_temperal_embedding = nn.ParameterList(
+                nn.Parameter(torch.zeros(1, 1, enc['width']), requires_grad=False) for _ in range(n_emb))
+        # the shipped default decoder (reference model.py:34-40)
+        self.decoder = GeneratorWithBeamSearch(eos_index=self.eos_index, max_steps=1024, beam_size=4,
+                                               length_penalty=0.6)
+        self._cfg = _lib.Config(
+            image_size=self.image_size, patch=enc['patch'], enc_width=enc['width'], enc_layers=enc['layers'],
+            enc_heads=enc['heads'], dec_hidden=HIDDEN, dec_layers=DEC_LAYERS, dec_heads=DEC_HEADS, dec_ffn=FFN,
+            vocab=VOCAB, max_positions=MAX_POS, num_frames_emb=n_emb, sos_id=self.sos_index, eos_id=self.eos_index)
+        self._engine = None
+        self._engine_device = None
+        self._weights_sig = None
+
+    # ---------------------------------------------------------------- engine plumbing
+    def _device(self):
+        return self.textual.embedding.words.weight.device
+
+    def _weights_signature(self):
+        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+
+    def _ensure_engine(self):
+        dev = self._device()
+        if dev.type != 'cuda':
+            raise RuntimeError('the gitb200 engine runs on CUDA devices only (sm_100a); call model.cuda() first. '
+                               'There is no CPU path.')
+        lib = _lib.load()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if self._engine is None or self._engine_device != dev:
+            self.release()
+            h = ctypes.c_void_p()
+            _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
+            self._engine, self._engine_device, self._weights_sig = h, dev, None
+        sig = self._weights_signature()
+        if sig != self._weights_sig:
+            for key, p in self.state_dict(keep_vars=True).items():
+                t = p.detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.gitb200_set_weight(self._engine, key.encode(), t.data_ptr(), shape, t.dim(), _lib.F32,
+                                                  stream), self._engine, 'set_weight(%s)' % key)
+            _lib.check(lib.gitb200_finalize_weights(self._engine, stream), self._engine, 'finalize_weights')
+            self._weights_sig = sig
+        return lib, stream
+
+    def release(self):
+        if self._engine is not None:
+            _lib.load().gitb200_destroy(self._engine)
+            self._engine = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return int(_lib.load().gitb200_launch_count(self._engine)) if self._engine is not None else 0
+
+    def _search_struct(self):
+        d = self.decoder
+        if isinstance(d, AutoRegressiveBeamSearch):
+            return _lib.Search(mode=_lib.SEARCH_GREEDY, max_steps=d.max_steps, beam_size=1, per_node_beam=1,
+                               length_penalty=1.0)
+        if isinstance(d, GeneratorWithBeamSearch):
+            return _lib.Search(mode=_lib.SEARCH_BEAM, max_steps=d.max_steps, beam_size=d.beam_size,
+                               per_node_beam=d.per_node_beam_size, length_penalty=float(d.length_penalty))
+        raise TypeError('model.decoder must be an AutoRegressiveBeamSearch or GeneratorWithBeamSearch of this package')
+
+    def _pack_images(self, image):
+        """-> (fp32 contiguous [frames*B,3,S,S] on device, B, frames) ; frames = 0 for a bare tensor."""
+        dev = self._device()
+        if isinstance(image, (list, tuple)):
+            frames = len(image)
+            ims = [im.to(device=dev, dtype=torch.float32) for im in image]
+            B = ims[0].shape[0]
+            x = ims[0].contiguous() if frames == 1 else torch.stack(ims, dim=0).contiguous()
+        else:
+            frames = 0
+            x = image.to(device=dev, dtype=torch.float32).contiguous()
+            B = x.shape[0]
+        S = self.image_size
+        if tuple(x.shape[-3:]) != (3, S, S):
+            raise NotImplementedError(
+                'input resolution %s != %d: runtime positional-embedding interpolation (reference '
+                'layers/CLIP/model.py:245-251) is not implemented' % (tuple(x.shape[-2:]), S))
+        return x, B, frames
+
+    # ---------------------------------------------------------------- the reference surface
+    @torch.no_grad()
+    def forward(self, batch, forced_tokens=None, return_step_logits=False):
+        """`model(batch)` of the reference in eval mode: CaptioningModel.forward -> infer.
+
+        batch: {'image': FloatTensor[B,3,H,W] | [FloatTensor[B,3,H,W]] * frames, 'prefix'?: LongTensor[1,P]}
+        forced_tokens / return_step_logits are parity-test hooks (teacher forcing, raw per-step logits).
+        """
+        if self.training:
+            raise NotImplementedError('training (loss / SCST branches) is out of scope: call model.eval()')
+        if 'image' not in batch:
+            raise NotImplementedError("batch without 'image' is not supported")
+        if 'context' in batch:
+            raise NotImplementedError("'context' batches are not produced by the reference inference path")
+        lib, stream = self._ensure_engine()
+        dev = self._device()
+        x, B, frames = self._pack_images(batch['image'])
+        sp = self._search_struct()
+        prefix, P = None, 0
+        if 'prefix' in batch:
+            assert len(batch['prefix']) == 1, 'not supported'      # reference layers/decoder.py:988
+            if B != 1:
+                raise AssertionError('not supported: a prefix needs batch size 1')
+            prefix = batch['prefix'].to(device=dev, dtype=torch.long).contiguous().view(-1)
+            P = prefix.numel()
+        tokens = torch.empty((B, sp.max_steps), dtype=torch.long, device=dev)
+        n_lp = B
+        logprobs = torch.empty((n_lp,), dtype=torch.float32, device=dev)
+        out_len = ctypes.c_int32(0)
+        forced = None
+        if forced_tokens is not None:
+            forced = forced_tokens.to(device=dev, dtype=torch.long).contiguous()
+            assert tuple(forced.shape) == (B, sp.max_steps)
+        step_logits = None
+        if return_step_logits:
+            rows = B * (sp.beam_size if sp.mode == _lib.SEARCH_BEAM else 1)
+            step_logits = torch.zeros((sp.max_steps - max(P, 1), rows, VOCAB), dtype=torch.float32, device=dev)
+        _lib.check(lib.gitb200_generate(
+            self._engine, x.data_ptr(), B, frames, prefix.data_ptr() if prefix is not None else None, P,
+            ctypes.byref(sp), forced.data_ptr() if forced is not None else None, tokens.data_ptr(),
+            logprobs.data_ptr(), ctypes.byref(out_len), step_logits.data_ptr() if step_logits is not None else None,
+            stream), self._engine, 'generate')
+        n = out_len.value
+        if sp.mode == _lib.SEARCH_GREEDY:
+            if n < 0:   # every first token was EOS (reference layers/decoder.py:279-291)
+                warnings.warn('Empty captions predicted. You may want to increase beam size or ensure your step '
+                              'function is working properly.', RuntimeWarning)
+                pred = tokens[:, max(P, 1):max(P, 1) + 1]
+                lp = logprobs[:, None]
+            else:
+                pred = tokens[:, :n]
+                lp = logprobs
+                if P:
+                    pred = pred[:, P:]                              # reference layers/decoder.py:1004-1006
+        else:
+            pred = tokens[:, P:] if P else tokens
+            lp = logprobs[:, None]
+        out = {'predictions': pred, 'logprobs': lp}
+        if return_step_logits:
+            out['step_logits'] = step_logits
+        return out
+
+    # ---------------------------------------------------------------- parity hooks (intermediate activations)
+    @torch.no_grad()
+    def encode_image(self, image):
+        """Image features as the decoder sees them: [B, frames*L, d] fp32 (reference layers/decoder.py:846-857)."""
+        lib, stream = self._ensure_engine()
+        x, B, frames = self._pack_images(image)
+        enc = ENCODER_CFG[self.param.get('image_encoder_type', 'CLIPViT_B_16')]
+        L = (self.image_size // enc['patch']) ** 2 + 1
+        nf = max(frames, 1)
+        if frames and self.num_image_with_embedding:
+            nf = min(nf, self.num_image_with_embedding)
+        feats = torch.empty((B, nf * L, enc['width']), dtype=torch.float32, device=x.device)
+        self._m_tokens = nf * L
+        _lib.check(lib.gitb200_encode(self._engine, x.data_ptr(), B, frames, feats.data_ptr(), stream), self._engine,
+                   'encode')
+        return feats
+
+    @torch.no_grad()
+    def prefill(self, batch_size, beam=1):
+        """visual_projection output [B, M, 768] fp32 after the last encode_image; fills the image K/V cache."""
+        lib, stream = self._ensure_engine()
+        M = self._last_M(batch_size)
+        out = torch.empty((batch_size, M, HIDDEN), dtype=torch.float32, device=self._device())
+        _lib.check(lib.gitb200_prefill(self._engine, batch_size, beam, out.data_ptr(), stream), self._engine, 'prefill')
+        return out
+
+    def _last_M(self, batch_size):
+        return self._m_tokens
+
+    @torch.no_grad()
+    def decoding_step(self, tokens, pos, beam_idx=None):
+        """Raw last-position logits [rows, V] for one new token per row at text position `pos`."""
+        lib, stream = self._ensure_engine()
+        tokens = tokens.to(device=self._device(), dtype=torch.long).contiguous()
+        rows = tokens.numel()
+        logits = torch.empty((rows, VOCAB), dtype=torch.float32, device=self._device())
+        bi = None
+        if beam_idx is not None:
+            bi = beam_idx.to(device=self._device(), dtype=torch.int32).contiguous()
+        _lib.check(lib.gitb200_decode_step(self._engine, tokens.data_ptr(), bi.data_ptr() if bi is not None else None,
+                                           rows, int(pos), logits.data_ptr(), stream), self._engine, 'decode_step')
+        return logits
+
+
+def get_git_model(tokenizer, param):
+    """Same signature and `param` keys as reference model.py:9 (`image_encoder_type`, `test_crop_size`,
+    `visual_feature_size`, `num_image_with_embedding`); reads only `tokenizer.cls_token_id/sep_token_id`."""
+    return GitB200CaptioningModel(tokenizer, param)

@@ -1,0 +1,147 @@
+/* gitb200 -- C ABI of the B200-native GIT captioning engine (libgitb200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference is 100 % Python/PyTorch
+ * (there is no FFI of its own), so the "binding a maintainer would add" is a ctypes stub
+ * (INTEGRATION.md); each entry point names the reference function it replaces.  Paths are relative to
+ * /root/reference/generativeimage2text/.
+ *
+ * Conventions
+ *   - plain C types only; every `dev` pointer is a CUDA device pointer owned by the caller
+ *     (e.g. `tensor.data_ptr()`), every `host` pointer is ordinary host memory;
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); entry points do
+ *     not synchronise unless documented;
+ *   - return 0 on success, non-zero on error; `gitb200_last_error` returns a message for the handle
+ *     (or for the last failed `gitb200_create` when h == NULL); nothing throws across the ABI;
+ *   - one engine per device and per thread of use (the reference model object is not re-entrant
+ *     either: layers/decoder.py:991 stores per-call state on the module).
+ */
+#ifndef GITB200_H_
+#define GITB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gitb200_engine gitb200_engine;
+
+/* Model geometry.  Mirrors what `get_git_model(tokenizer, param)` hard-codes / reads from `param`
+ * (model.py:9-61, 63-91): encoder = CLIP ViT-B/16 or ViT-L/14, decoder = 6 x 768 BERT-style layers. */
+typedef struct gitb200_config {
+  int32_t image_size;      /* param['test_crop_size'] (224)                          model.py:13  */
+  int32_t patch;           /* 16 (CLIPViT_B_16) / 14 (CLIPViT_L_14)                   model.py:64-67 */
+  int32_t enc_width;       /* 768 / 1024                                                           */
+  int32_t enc_layers;      /* 12 / 24                                                              */
+  int32_t enc_heads;       /* 12 / 16                                                              */
+  int32_t dec_hidden;      /* 768                                                     model.py:17  */
+  int32_t dec_layers;      /* 6                                                       model.py:18  */
+  int32_t dec_heads;       /* 12                                                      model.py:19  */
+  int32_t dec_ffn;         /* 3072                                                    model.py:20  */
+  int32_t vocab;           /* 30522                                                   model.py:16  */
+  int32_t max_positions;   /* 1024                                                    model.py:21  */
+  int32_t num_frames_emb;  /* param['num_image_with_embedding'] or 0                  model.py:59  */
+  int32_t sos_id;          /* tokenizer.cls_token_id                                  model.py:54  */
+  int32_t eos_id;          /* tokenizer.sep_token_id                                  model.py:35,55 */
+} gitb200_config;
+
+/* Search configuration: the two decoders of model.py:27-40. */
+enum { GITB200_SEARCH_GREEDY = 0, GITB200_SEARCH_BEAM = 1 };
+typedef struct gitb200_search {
+  int32_t mode;            /* GREEDY = AutoRegressiveBeamSearch(beam 1, per-node 1)  layers/decoder.py:208-440
+                              BEAM   = GeneratorWithBeamSearch                        layers/decoder.py:1056-1341 */
+  int32_t max_steps;       /* output length cap incl. start tokens (40 in BASELINE.json; 1024 stock) */
+  int32_t beam_size;       /* 4                                                       model.py:38  */
+  int32_t per_node_beam;   /* 2                                                       layers/decoder.py:1062 */
+  float length_penalty;    /* 0.6                                                     model.py:39  */
+} gitb200_search;
+
+enum { GITB200_F32 = 0, GITB200_BF16 = 1, GITB200_I64 = 2 };
+
+/* Replaces: get_git_model (construction)                                            model.py:9-61 */
+int gitb200_create(const gitb200_config* cfg, int device, gitb200_engine** out);
+void gitb200_destroy(gitb200_engine* h);
+const char* gitb200_last_error(const gitb200_engine* h);
+/* ABI version of the library (bumped on any signature change). */
+int gitb200_abi_version(void);
+
+/* Replaces: torch_common.load_state_dict -> module parameters           torch_common.py:93-145.
+ * `ref_key` is the reference state-dict key (e.g. "image_encoder.conv1.weight"); `dev_ptr` an fp32
+ * device tensor of `shape[ndim]`.  The engine repacks into its own layouts (bf16 GEMM operands,
+ * fused QKV, padded patch kernel); the caller keeps ownership of the source and may free it after
+ * gitb200_finalize_weights returns.  Unknown keys return an error; "image_encoder.proj" and
+ * "textual.output.weight" (tied) are accepted and ignored. */
+int gitb200_set_weight(gitb200_engine* h, const char* ref_key, const void* dev_ptr, const int64_t* shape,
+                       int ndim, int dtype, void* stream);
+/* Checks that every tensor of the geometry has been provided. Synchronises the stream. */
+int gitb200_finalize_weights(gitb200_engine* h, void* stream);
+
+/* Replaces: CaptioningModel.forward_one image branch = VisualTransformer.forward per frame
+ * (+ img_temperal_embedding, token-axis concat)      layers/decoder.py:846-857, layers/CLIP/model.py:240-268.
+ * images_dev: fp32 [frames][B,3,S,S] contiguous (frames >= 1; frame f at offset f*B*3*S*S).
+ * feats_out_dev: fp32 [B, frames*L, enc_width] or NULL (kept internally for gitb200_prefill). */
+int gitb200_encode(gitb200_engine* h, const float* images_dev, int batch, int frames, float* feats_out_dev,
+                   void* stream);
+
+/* Replaces: visual_projection + the image rows of BertEncoderAsDecoder, computed once (KV cache)
+ *                                      layers/decoder.py:535, 92-174; layers/bert/modeling_bert.py:92-334.
+ * Uses the features of the last gitb200_encode. vproj_out_dev: fp32 [B, M, 768] or NULL. */
+int gitb200_prefill(gitb200_engine* h, int batch, int beam, float* vproj_out_dev, void* stream);
+
+/* Replaces: CaptioningModel.decoding_step (one new token per row)       layers/decoder.py:1013-1054.
+ * tokens_dev: int64 [rows] newest token of each row (rows = batch*beam), appended at text position
+ * `pos`; beam_idx_dev (int32 [rows], may be NULL) re-orders the text KV cache first
+ * (layers/decoder.py:1231).  logits_out_dev: fp32 [rows, vocab] raw last-position logits. */
+int gitb200_decode_step(gitb200_engine* h, const int64_t* tokens_dev, const int32_t* beam_idx_dev, int rows,
+                        int pos, float* logits_out_dev, void* stream);
+
+/* Replaces: CaptioningModel.forward / infer + decoder.search            layers/decoder.py:838-1011,
+ * AutoRegressiveBeamSearch.search :224-440, GeneratorWithBeamSearch.search :1083-1290.
+ * images_dev as gitb200_encode.  prefix_dev: int64 [P] start tokens (NULL/0 -> [sos]); reference asserts
+ * batch == 1 with a prefix (layers/decoder.py:988).
+ * forced_dev (int64 [B, max_steps] or NULL): teacher forcing for parity tests -- at every step the
+ * engine records its own choice but feeds forced[:, t] as the next input (greedy only).
+ * tokens_out_dev: int64 [B, max_steps] (incl. start tokens; EOS padded);  logprobs_out_dev: fp32 [B];
+ * out_len_host: number of valid columns (greedy may stop early, layers/decoder.py:319), written after
+ * an internal stream synchronise (the only sync of the call).
+ * step_logits_dev: optional fp32 [steps, rows, vocab] dump of raw step logits (parity hook). */
+int gitb200_generate(gitb200_engine* h, const float* images_dev, int batch, int frames, const int64_t* prefix_dev,
+                     int prefix_len, const gitb200_search* search, const int64_t* forced_dev,
+                     int64_t* tokens_out_dev, float* logprobs_out_dev, int32_t* out_len_host,
+                     float* step_logits_dev, void* stream);
+
+/* Same as gitb200_generate but with HOST buffers (pinned or pageable): copies the pixels host->device,
+ * runs, copies tokens / logprobs back and synchronises.  This is the call a C host makes. */
+int gitb200_generate_host(gitb200_engine* h, const float* images_host, int batch, int frames,
+                          const int64_t* prefix_host, int prefix_len, const gitb200_search* search,
+                          int64_t* tokens_out_host, float* logprobs_out_host, int32_t* out_len_host, void* stream);
+
+/* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
+int64_t gitb200_launch_count(const gitb200_engine* h);
+/* Enable/disable CUDA-graph replay of the decode step (default on). */
+int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value);
+
+/* ---- single-kernel entry points (unit tests, micro-benchmarks, ncu) -------------------------------- */
+/* C = A[M,K] * W[N,K]^T (+bias) (+act: 0 none, 1 QuickGELU, 2 erf-GELU) (+resid fp32 [M,N]).
+ * a_dev, w_dev bf16; out fp32 or bf16.  transposed != 0 runs the swap-AB skinny path used by the decode
+ * step (a_dev = activations [M<=256,K], w_dev = weight [N,K], out[M,N]); k_splits > 1 accumulates with
+ * atomics into a zeroed fp32 out (transposed only). bn: tile width override (0 = heuristic). */
+int gitb200_op_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
+                    void* out_dev, int M, int N, int K, int act, int out_bf16, int transposed, int k_splits,
+                    int bn, void* stream);
+/* y = LayerNorm(x (+bias) (+resid)) * gamma + beta over the last dim D (768 or 1024), fp32 in,
+ * fp32 and/or bf16 out (either may be NULL). */
+int gitb200_op_layernorm(const float* x_dev, const float* bias_dev, const float* resid_dev, const float* gamma_dev,
+                         const float* beta_dev, float eps, float* out_f32_dev, void* out_bf16_dev, int rows, int D,
+                         void* stream);
+/* Non-causal multi-head attention over packed bf16 rows: q/k/v [B, S, H*64] with the given row strides
+ * (elements) and batch strides; out bf16 [B, S, H*64]. softmax(q k^T / 8) v. */
+int gitb200_op_attention(const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int B, int S, int H,
+                         long long q_row_stride, long long kv_row_stride, long long q_batch_stride,
+                         long long kv_batch_stride, long long out_row_stride, long long out_batch_stride,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GITB200_H_ */
