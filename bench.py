@@ -1,0 +1,310 @@
+"""bench.py -- captions/sec of the GIT captioning hot path (BASELINE.json metric).
+
+A "step" is one `model({'image': x})` call over one batch of synthetic 224x224 images: CLIP-ViT encoder ->
+visual projection -> image-row prefill of the 6 decoder layers -> 39 KV-cached greedy decode steps
+(max_len 40), i.e. the reference's `CaptioningModel.forward` in eval mode with its greedy decoder
+(reference model.py:27-33).  N=1 workload = BASELINE.json configs[1]: GIT_BASE, batch 64, one B200.
+Random-init weights of that architecture (reference initialiser distributions) and synthetic pixels.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Multi-GPU (torchrun, one rank per GPU): every rank captions its own batch (weak scaling, image-wise
+sharding, reference inference.py:165-169) and the timed region ends with ONE NCCL all_gather of the
+finished token ids.  `--impl reference` times the reference's own CPU algorithm (the as-shipped, no-KV-cache
+restatement in oracle/git_oracle.py -- the Python reference itself cannot travel to the GPU box) on the
+host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'captions/sec (greedy, max_len=40) GIT_BASE batch64'
+UNIT = 'captions/s'
+MAX_STEPS = 40
+BATCH = 64
+
+
+class Tok:
+    cls_token_id, sep_token_id = 101, 102
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_tflops=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained'),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def cpu_baseline_run(sample_batch, steps, warmup, threads=None):
+    """The reference's CPU path as shipped (full [image || text] recompute every step), fp32, all host threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import git_oracle
+    from generativeimage2text_b200.synthetic import synthetic_state_dict, synthetic_images
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = synthetic_state_dict({}, 0, 'init')
+    img = synthetic_images(sample_batch, 0, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = git_oracle.generate(sd, {}, {'image': img}, 'greedy', MAX_STEPS, cached=False)
+        dt = time.perf_counter() - t0
+        assert out['predictions'].shape == (sample_batch, MAX_STEPS)
+        if i >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return sample_batch / mean, mean, threads
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    sample = 4
+    value, sec, threads = cpu_baseline_run(sample, max(1, min(args.steps, 3)), 1 if args.warmup > 0 else 0)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'GIT_BASE greedy max_len=40, synthetic 224x224, random-init weights', 'global_batch': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': 'oracle/git_oracle.py as-shipped mode (no KV cache, fp32 torch CPU ops): batch of %d images '
+                                   'per step instead of 64 (same per-image work; CPU throughput is batch-insensitive here)' % sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='gitb200')
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-micro', action='store_true')
+    args = ap.parse_args()
+    rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    __graft_entry__.build()
+    from generativeimage2text_b200 import _lib
+    from generativeimage2text_b200.model import get_git_model, AutoRegressiveBeamSearch
+    from generativeimage2text_b200.sharding import gather_captions
+    from generativeimage2text_b200.synthetic import synthetic_state_dict, synthetic_images
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    B = args.batch
+    model = get_git_model(Tok(), {})
+    model.load_state_dict(synthetic_state_dict({}, 0, 'init'), strict=True)
+    model = model.to(dev).eval()
+    model.decoder = AutoRegressiveBeamSearch(102, max_steps=MAX_STEPS, beam_size=1, per_node_beam_size=1,
+                                             fix_missing_prefix=True)
+    img_host = synthetic_images(B, 0, 1234 + rank).contiguous().pin_memory()
+    img_dev = img_host.to(dev)
+    stream = torch.cuda.Stream(device=dev)
+    n_total = B * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step_device():
+        out = model({'image': img_dev})
+        toks, lps = out['predictions'], out['logprobs']
+        if world > 1:
+            toks, lps = gather_captions(toks, lps, n_total)
+        return toks
+
+    # ---------------- device-resident timing (`value`) ----------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            toks = one_step_device()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = model.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            toks = one_step_device()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = model.launch_count() - launches0
+        assert toks.shape[0] == n_total and toks.shape[1] == MAX_STEPS
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = n_total * args.steps / (ms / 1e3)
+
+    # ---------------- end to end through the C ABI with HOST buffers (`e2e`) ----------------
+    lib, _ = model._ensure_engine()
+    sp = model._search_struct()
+    tok_host = torch.empty((B, MAX_STEPS), dtype=torch.long).pin_memory()
+    lp_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    n_out = ctypes.c_int32(0)
+
+    def one_step_host():
+        _lib.check(lib.gitb200_generate_host(model._engine, img_host.data_ptr(), B, 0, None, 0, ctypes.byref(sp),
+                                             tok_host.data_ptr(), lp_host.data_ptr(), ctypes.byref(n_out),
+                                             stream.cuda_stream), model._engine, 'generate_host')
+        if world > 1:
+            gather_captions(tok_host.to(dev, non_blocking=True), lp_host.to(dev, non_blocking=True), n_total)
+
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            one_step_host()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            one_step_host()
+        e1.record(stream)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = t.item()
+    e2e_value = n_total * args.steps / (ms_e2e / 1e3)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # ---------------- roofline of the dominant kernel, measured live ----------------
+    peaks = measured_peaks()
+    roofline = None
+    extra = {}
+    if rank == 0 and not args.no_micro:
+        # dominant kernel = gemm_bf16_tcgen05 (profiles/: ~2/3 of the step); its largest instance is the ViT MLP
+        # c_fc GEMM [B*197, 768] x [768, 3072] (+bias +QuickGELU, bf16 out): algorithmic FLOPs = 2*M*N*K.
+        M, N, K = B * 197, 3072, 768
+        a = (torch.randn(M, K, device=dev) * 1.0).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) * 0.03).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+        with torch.cuda.stream(stream):
+            def gemm():
+                rc = lib.gitb200_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), None, out.data_ptr(), M, N, K, 1, 1, 0, 1,
+                                         0, stream.cuda_stream)
+                assert rc == 0, _lib.last_error(None)
+            for _ in range(3):
+                gemm()
+            durs = []
+            for _ in range(10):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                gemm()
+                e1.record(stream)
+                e1.synchronize()
+                durs.append(e0.elapsed_time(e1))
+        avg_ms = sum(durs) / len(durs)
+        flops = 2.0 * M * N * K
+        achieved = flops / (avg_ms / 1e3) / 1e12
+        roofline = {'kernel': 'gemm_bf16_tcgen05<BN> (ViT mlp.c_fc shape %dx%dx%d, bias+QuickGELU epilogue)' % (M, N, K),
+                    'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                    'frac': achieved / peaks['bf16_tflops'], 'traffic': None, 'avg_launch_ms': avg_ms,
+                    'peak_source': peaks['source'] + ', burst bf16 figure (kernel timed alone, L2 flushed between launches)'}
+        extra['whole_step'] = {
+            'algorithmic_tflop_per_step': 58.1e9 * B / 1e12,
+            'achieved_tflops_whole_step': 58.1e9 * B * args.steps / (ms / 1e3) / 1e12 / world * world,
+        }
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, sec, threads = cpu_baseline_run(4, 1, 0)
+        cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': 'one batch of 4 images through oracle/git_oracle.py in as-shipped mode (no KV cache, fp32, %.1f s); '
+                         'same per-image work as the batch-64 workload' % sec}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'GIT_BASE (CLIP ViT-B/16 + 6x768 decoder) greedy max_len=40, batch %d synthetic 224x224 '
+                                   'per GPU, random-init weights' % B,
+                       'global_batch': n_total, 'per_gpu_batch': B, 'parallelism': 'image-parallel x%d + 1 all_gather' % world,
+                       'l2': 'inputs larger than L2: each step streams ~0.3 GB weights + 0.23 GB image K/V + activations (> 126 MB)',
+                       'compute': 'bf16 operands, fp32 accumulate, fp32 residual stream'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': img_host.numel() * 4, 'd2h_bytes_per_step': tok_host.numel() * 8 + lp_host.numel() * 4},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+            'roofline': roofline,
+            'cpu_baseline': cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -121,6 +121,8 @@ struct gitb200_engine {
   cudaGraphExec_t step_graph = nullptr;
   std::vector<long long> step_graph_key;
   int64_t launches_per_step = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t own_event = nullptr;
 };
 
 static int fail(gitb200_engine* h, const char* fmt, ...) {
@@ -427,6 +429,8 @@ extern "C" void gitb200_destroy(gitb200_engine* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  if (h->own_event) cudaEventDestroy(h->own_event);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   release_all(h);
   delete h;
 }
