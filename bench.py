@@ -89,7 +89,7 @@ def cpu_baseline_run(sample_batch, steps, warmup, threads=None):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import git_oracle
     from generativeimage2text_b200.synthetic import synthetic_state_dict, synthetic_images
-    threads = threads or os.cpu_count()
+    threads = threads or min(os.cpu_count(), 16)
     torch.set_num_threads(threads)
     sd = synthetic_state_dict({}, 0, 'init')
     img = synthetic_images(sample_batch, 0, 1234)

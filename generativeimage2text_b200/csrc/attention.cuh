@@ -200,24 +200,46 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
   f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
 
+// Online-softmax state of one 8-lane key group for one query: running max m, running sum l, 8 output dims.
+__device__ __forceinline__ void dec_attn_update(float (&sc)[4], const uint4 (&w)[4], float& m, float& l, float (&acc)[8]) {
+  float m_new = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), m);
+  if (m_new == -INFINITY) return;  // nothing valid seen yet
+  const float scale = __expf(m - m_new);
+  float p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __expf(sc[i] - m_new);
+  l = l * scale + (p[0] + p[1]) + (p[2] + p[3]);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) acc[d] *= scale;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float f[8];
+    bf16x8_to_f32(w[i], f);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] = fmaf(p[i], f[d], acc[d]);
+  }
+  m = m_new;
+}
+
+// grid (heads, images); 128 threads = 16 key groups x 8 lanes (8 head dims each, 128-bit loads).
+// Single pass: K and V rows of a key block are requested together (8 x 16 B in flight per thread), scores are
+// folded into per-group online-softmax states that are merged at the end (flash-decoding style).
 template <int NQ>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p) {
   if (p.state != nullptr && p.state->finished) return;
-  extern __shared__ float dyn_smem[];
   const int pos = (p.state != nullptr) ? p.state->pos : p.pos_fixed;
   const int n_txt = pos + 1;
-  const int Sk = p.M + n_txt;
-  float* sc = dyn_smem;  // [NQ][Sk]
   __shared__ float q_s[NQ][64];
-  __shared__ float inv_sum[NQ];
-  __shared__ float red[4][NQ][64];
+  __shared__ float red_m[4][NQ];
+  __shared__ float red_l[4][NQ];
+  __shared__ float red_acc[4][NQ][64];
 
   const int h = blockIdx.x;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int D = p.D;
 
-  // ---- phase 0: q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V ----
+  // ---- q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V (bf16) ----
   for (int qi = 0; qi < NQ; ++qi) {
     const int r = b * NQ + qi;
     const float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
@@ -231,156 +253,128 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
   }
   __syncthreads();
 
-  const int grp = tid >> 3;  // 16 key groups
-  const int gl = tid & 7;    // 8 lanes x 8 dims
+  const int grp = tid >> 3;
+  const int gl = tid & 7;
   float qreg[NQ][8];
+  float m_run[NQ], l_run[NQ], acc[NQ][8];
 #pragma unroll
-  for (int qi = 0; qi < NQ; ++qi)
+  for (int qi = 0; qi < NQ; ++qi) {
+    m_run[qi] = -INFINITY;
+    l_run[qi] = 0.f;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) qreg[qi][d] = q_s[qi][gl * 8 + d];
+    for (int d = 0; d < 8; ++d) {
+      qreg[qi][d] = q_s[qi][gl * 8 + d];
+      acc[qi][d] = 0.f;
+    }
+  }
 
-  // ---- phase 1: scores ---------------------------------------------------------------------------
+  // ---- image keys: shared by the NQ beams of this image ----
   {
     const __nv_bfloat16* kb = p.img_k + static_cast<long long>(b) * p.M * D + h * 64 + gl * 8;
+    const __nv_bfloat16* vb = p.img_v + static_cast<long long>(b) * p.M * D + h * 64 + gl * 8;
     for (int base = 0; base < p.M; base += 64) {  // uniform trip count: the shuffles below stay converged
-      const int s0 = base + grp;
-      uint4 u[4];
+      uint4 u[4], w[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int s = s0 + 16 * i;
-        u[i] = (s < p.M) ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
+        const int s = base + grp + 16 * i;
+        const bool ok = s < p.M;
+        u[i] = ok ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
+        w[i] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
       }
+      float kf[4][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int s = s0 + 16 * i;
-        float f[8];
-        bf16x8_to_f32(u[i], f);
+      for (int i = 0; i < 4; ++i) bf16x8_to_f32(u[i], kf[i]);
 #pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) {
+      for (int qi = 0; qi < NQ; ++qi) {
+        float sc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
           float a = 0.f;
 #pragma unroll
-          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], f[d], a);
+          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[i][d], a);
           a += __shfl_xor_sync(0xffffffffu, a, 1);
           a += __shfl_xor_sync(0xffffffffu, a, 2);
           a += __shfl_xor_sync(0xffffffffu, a, 4);
-          if (gl == 0 && s < p.M) sc[qi * Sk + s] = a;
+          sc[i] = (base + grp + 16 * i < p.M) ? a : -INFINITY;
         }
+        dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
       }
     }
+  }
+  // ---- text keys: each beam row has its own history (through the src_row indirection) ----
 #pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) {
-      const int r = b * NQ + qi;
-      for (int j0 = 0; j0 < n_txt; j0 += 16) {  // uniform trip count: shuffles stay converged
-        const int j = j0 + grp;
-        float a = 0.f;
+  for (int qi = 0; qi < NQ; ++qi) {
+    const int r = b * NQ + qi;
+    for (int base = 0; base < n_txt; base += 64) {
+      uint4 u[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = base + grp + 16 * i;
         if (j < n_txt) {
           const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
-          const uint4 u = *reinterpret_cast<const uint4*>(p.txt_k + (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8);
-          float f[8];
-          bf16x8_to_f32(u, f);
-#pragma unroll
-          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], f[d], a);
+          const long long off = (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8;
+          u[i] = *reinterpret_cast<const uint4*>(p.txt_k + off);
+          w[i] = *reinterpret_cast<const uint4*>(p.txt_v + off);
+        } else {
+          u[i] = make_uint4(0, 0, 0, 0);
+          w[i] = make_uint4(0, 0, 0, 0);
         }
+      }
+      float sc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float kf[8];
+        bf16x8_to_f32(u[i], kf);
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[d], a);
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (gl == 0 && j < n_txt) sc[qi * Sk + p.M + j] = a;
+        sc[i] = (base + grp + 16 * i < n_txt) ? a : -INFINITY;
       }
+      dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
     }
   }
-  __syncthreads();
-
-  // ---- phase 2: softmax (one warp per query) -------------------------------------------------------
-  {
-    const int w = tid >> 5;
-    const int lane = tid & 31;
-    for (int qi = w; qi < NQ; qi += 4) {
-      float mx = -INFINITY;
-      for (int s = lane; s < Sk; s += 32) mx = fmaxf(mx, sc[qi * Sk + s]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int s = lane; s < Sk; s += 32) {
-        const float e = __expf(sc[qi * Sk + s] - mx);
-        sc[qi * Sk + s] = e;
-        sum += e;
+  // ---- merge the 16 group states: 4 groups of a warp by shuffles, the 4 warps through smem ----
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float m_o = __shfl_xor_sync(0xffffffffu, m_run[qi], o);
+      const float l_o = __shfl_xor_sync(0xffffffffu, l_run[qi], o);
+      const float m_n = fmaxf(m_run[qi], m_o);
+      const float sa = (m_run[qi] == -INFINITY) ? 0.f : __expf(m_run[qi] - m_n);
+      const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - m_n);
+      l_run[qi] = l_run[qi] * sa + l_o * sb;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float a_o = __shfl_xor_sync(0xffffffffu, acc[qi][d], o);
+        acc[qi][d] = acc[qi][d] * sa + a_o * sb;
       }
-      sum = warp_sum(sum);
-      if (lane == 0) inv_sum[qi] = 1.0f / sum;
+      m_run[qi] = m_n;
     }
-  }
-  __syncthreads();
-
-  // ---- phase 3: ctx = P V -----------------------------------------------------------------------------
-  float acc[NQ][8];
-#pragma unroll
-  for (int qi = 0; qi < NQ; ++qi)
-#pragma unroll
-    for (int d = 0; d < 8; ++d) acc[qi][d] = 0.f;
-  {
-    const __nv_bfloat16* vb = p.img_v + static_cast<long long>(b) * p.M * D + h * 64 + gl * 8;
-    for (int base = 0; base < p.M; base += 64) {
-      const int s0 = base + grp;
-      uint4 u[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int s = s0 + 16 * i;
-        u[i] = (s < p.M) ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int s = s0 + 16 * i;
-        if (s < p.M) {
-          float f[8];
-          bf16x8_to_f32(u[i], f);
-#pragma unroll
-          for (int qi = 0; qi < NQ; ++qi) {
-            const float pw = sc[qi * Sk + s];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) acc[qi][d] = fmaf(pw, f[d], acc[qi][d]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) {
-      const int r = b * NQ + qi;
-      for (int j = grp; j < n_txt; j += 16) {
-        const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
-        const uint4 u = *reinterpret_cast<const uint4*>(p.txt_v + (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8);
-        float f[8];
-        bf16x8_to_f32(u, f);
-        const float pw = sc[qi * Sk + p.M + j];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) acc[qi][d] = fmaf(pw, f[d], acc[qi][d]);
-      }
-    }
-  }
-  // reduce the 4 key groups of a warp, then the 4 warps
-#pragma unroll
-  for (int qi = 0; qi < NQ; ++qi)
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      float a = acc[qi][d];
-      a += __shfl_xor_sync(0xffffffffu, a, 8);
-      a += __shfl_xor_sync(0xffffffffu, a, 16);
-      acc[qi][d] = a;
-    }
-  {
-    const int w = tid >> 5;
-    const int lane = tid & 31;
     if (lane < 8) {
+      if (lane == 0) { red_m[warp][qi] = m_run[qi]; red_l[warp][qi] = l_run[qi]; }
 #pragma unroll
-      for (int qi = 0; qi < NQ; ++qi)
-#pragma unroll
-        for (int d = 0; d < 8; ++d) red[w][qi][lane * 8 + d] = acc[qi][d];
+      for (int d = 0; d < 8; ++d) red_acc[warp][qi][lane * 8 + d] = acc[qi][d];
     }
   }
   __syncthreads();
   for (int i = tid; i < NQ * 64; i += 128) {
     const int qi = i >> 6;
     const int d = i & 63;
-    const float v = (red[0][qi][d] + red[1][qi][d]) + (red[2][qi][d] + red[3][qi][d]);
-    p.ctx[static_cast<long long>(b * NQ + qi) * D + h * 64 + d] = __float2bfloat16_rn(v * inv_sum[qi]);
+    const float mm = fmaxf(fmaxf(red_m[0][qi], red_m[1][qi]), fmaxf(red_m[2][qi], red_m[3][qi]));
+    float l = 0.f, a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float sw = (red_m[w][qi] == -INFINITY) ? 0.f : __expf(red_m[w][qi] - mm);
+      l += red_l[w][qi] * sw;
+      a += red_acc[w][qi][d] * sw;
+    }
+    p.ctx[static_cast<long long>(b * NQ + qi) * D + h * 64 + d] = __float2bfloat16_rn(a / l);
   }
 }
 

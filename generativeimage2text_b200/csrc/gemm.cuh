@@ -36,6 +36,7 @@ struct GemmParams {
   int rows_per_batch;         // row map: m -> (m / rpb) * batch_stride[seg] + (m % rpb) + row_offset
   int row_offset;
   const int* skip;            // device flag: non-zero -> the whole launch is a no-op (finished decode)
+  unsigned long long* dbg;    // optional [8] %globaltimer stamps of CTA 0 (profiling aid; null in production)
 };
 
 template <int BN>
@@ -45,18 +46,23 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_WARPS = 8;                       // two per TMEM lane quadrant
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;      // warps 0-3: TMA / MMA / TMEM alloc / spare
+  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 128;  // per warp: 32 rows x 32 fp32, 16B-chunk XOR swizzle
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_LIMIT = 227 * 1024;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + BAR_BYTES;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
   static_assert((2 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier area");
+  static_assert(STAGES >= 3, "pipeline depth");
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmParams p) {
   using C = GemmCfg<BN>;
@@ -65,7 +71,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* sStage = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStage + C::STAGING_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -73,6 +80,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool dbg = (p.dbg != nullptr) && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = globaltimer_ns();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -85,7 +94,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], C::EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -97,6 +106,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();
 
   const int m_tiles = (p.M + C::BM - 1) / C::BM;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -147,6 +157,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (dbg && tile == 0 && kb == kb0) p.dbg[2] = globaltimer_ns();
           const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
           const uint32_t b_base = smem_u32(sB + stage * C::B_BYTES);
 #pragma unroll
@@ -161,13 +172,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         umma_commit(&tfull[accum]);  // accumulator complete -> epilogue
+        if (dbg && tile == 0) p.dbg[3] = globaltimer_ns();
         accum ^= 1;
         if (accum == 0) accum_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // 8 warps: warp w reads TMEM lanes 32*(w%4).. (hardware restriction) and the 32-column chunks
+    // c == (w-4)/4 (mod 2).  Normal mode transposes each 32x32 fp32 chunk through a per-warp swizzled
+    // staging buffer so that global loads (residual) and stores are fully coalesced 128-byte rows.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint8_t* stg = sStage + (warp - 4) * (32 * 128);
+    const uint32_t stg_u32 = smem_u32(stg);
     int accum = 0;
     uint32_t accum_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -177,70 +195,67 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n_blk = rem - m_blk * n_tiles;
       mbar_wait(&tfull[accum], accum_phase);
       tc_fence_after();
-      const int row = m_blk * C::BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      if (dbg && tile == 0 && warp == 4 && lane == 0) p.dbg[4] = globaltimer_ns();
+      const int row0 = m_blk * C::BM + q * 32;  // first row of this warp
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int n0 = n_blk * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN + c * 32, r);
         tmem_ld_wait();
         if (!p.transposed) {
-          float v[32];
+          // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = stg_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                         "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                         : "memory");
+          }
+          __syncwarp();
+          // phase 2: 8 lanes per row (4 columns each), 4 rows per instruction
+          const int c4 = lane & 7;
+          const int rsub = lane >> 3;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + c4);
+          const int seg = n0 / p.seg_n;
+          const int nn = n0 - seg * p.seg_n + c4 * 4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(bp + j);
-              v[4 * j + 0] += b4.x;
-              v[4 * j + 1] += b4.y;
-              v[4 * j + 2] += b4.z;
-              v[4 * j + 3] += b4.w;
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const int row = row0 + rr;
+            float4 v;
+            const uint32_t addr = stg_u32 + rr * 128 + ((c4 ^ (rr & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (p.act != ACT_NONE) {
+              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
             }
-          }
-          if (p.act != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          if (row_ok) {
-            if (p.resid != nullptr) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ld_resid + n0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r4 = rp[j];
-                v[4 * j + 0] += r4.x;
-                v[4 * j + 1] += r4.y;
-                v[4 * j + 2] += r4.z;
-                v[4 * j + 3] += r4.w;
+            if (row < p.M) {
+              if (p.resid != nullptr) {
+                const float4 r4 = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ld_resid + n0 + c4 * 4);
+                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+              }
+              const int b = row / p.rows_per_batch;
+              const int s = row - b * p.rows_per_batch;
+              const long long orow = static_cast<long long>(b) * p.batch_stride[seg] + s + p.row_offset;
+              if (p.out_bf16) {
+                uint2 o;
+                o.x = pack_bf16(v.x, v.y);
+                o.y = pack_bf16(v.z, v.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + orow * p.ldo[seg] + nn) = o;
+              } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + orow * p.ldo[seg] + nn) = v;
               }
             }
-            const int seg = n0 / p.seg_n;
-            const int nn = n0 - seg * p.seg_n;
-            const int b = row / p.rows_per_batch;
-            const int s = row - b * p.rows_per_batch;
-            const long long orow = static_cast<long long>(b) * p.batch_stride[seg] + s + p.row_offset;
-            if (p.out_bf16) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + orow * p.ldo[seg] + nn);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-                o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                op[j] = o;
-              }
-            } else {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + orow * p.ldo[seg] + nn);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
           }
+          __syncwarp();
         } else {
-          // transposed: lane = output feature `row`, register j = activation row n0 + j
+          // transposed: lane = output feature, register j = activation row n0 + j (stores coalesce over lanes)
+          const int row = row0 + lane;
+          const bool row_ok = row < p.M;
           const float bv = (p.bias != nullptr && row_ok && split == 0) ? __ldg(p.bias + row) : 0.0f;
           if (row_ok) {
 #pragma unroll
@@ -272,6 +287,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);

@@ -112,6 +112,7 @@ struct gitb200_engine {
   DevBuf xd_t, hd_t, qkv_t, ctx_t, t_t, u_t, logits;        // decode step
   DevBuf state, next_token, logprob_sum, tokens_i64, stage_img, stage_tok, stage_lp, prefix_dev;
   DevBuf beam_ws;                                           // beam-search bookkeeping (search.cuh)
+  DevBuf sel_ws;                                            // greedy selection partials
   int cur_B = 0, cur_frames = 0, cur_M = 0, cur_beam = 1, T_alloc = 0, cur_rows = 0, cur_src = 0;
 
   EncodeTiledFn encode_tiled = nullptr;
@@ -221,7 +222,7 @@ static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st)
   const int n_tiles = (c.p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles * c.p.k_splits;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  gemm_bf16_tcgen05<BN><<<grid, 256, C::SMEM_BYTES, st>>>(ta, tb, c.p);
+  gemm_bf16_tcgen05<BN><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, c.p);
   CKL(h, "gemm_bf16_tcgen05");
   return 0;
 }
@@ -319,11 +320,29 @@ static LnParams ln_params(const float* x, const float* bias, const float* resid,
   return p;
 }
 
+template <int NW>
+static void launch_flash(const AttnParams& p, cudaStream_t st) {
+  dim3 grid((p.S + NW * 16 - 1) / (NW * 16), p.H, p.B);
+  flash_attn_kernel<NW><<<grid, NW * 32, 0, st>>>(p);
+}
 static int launch_attention(gitb200_engine* h, const AttnParams& ap, cudaStream_t st) {
   AttnParams p = ap;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((p.S + 63) / 64, p.H, p.B);
-  flash_attn_kernel<4><<<grid, 128, 0, st>>>(p);
+  // query rows per CTA = 16 * NW: least padding first, then the larger tile (K/V are re-read per query tile)
+  const int cands[4] = {8, 7, 6, 4};
+  int best = 4;
+  long long best_pad = 1LL << 60;
+  for (int i = 0; i < 4; ++i) {
+    const int rows = cands[i] * 16;
+    const long long padded = static_cast<long long>((p.S + rows - 1) / rows) * rows;
+    if (padded < best_pad) { best_pad = padded; best = cands[i]; }
+  }
+  switch (best) {
+    case 8: launch_flash<8>(p, st); break;
+    case 7: launch_flash<7>(p, st); break;
+    case 6: launch_flash<6>(p, st); break;
+    default: launch_flash<4>(p, st); break;
+  }
   CKL(h, "flash_attn_kernel");
   return 0;
 }
@@ -412,7 +431,7 @@ static void release_all(gitb200_engine* h) {
                     &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->txt_kv, &h->src_row[0],
                     &h->src_row[1], &h->xd_t, &h->hd_t, &h->qkv_t, &h->ctx_t, &h->t_t, &h->u_t, &h->logits, &h->state,
                     &h->next_token, &h->logprob_sum, &h->tokens_i64, &h->stage_img, &h->stage_tok, &h->stage_lp,
-                    &h->prefix_dev, &h->beam_ws};
+                    &h->prefix_dev, &h->beam_ws, &h->sel_ws};
   for (DevBuf* b : bufs) b->release();
   for (auto& l : h->enc) {
     DevBuf* lb[] = {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.ln2g, &l.ln2b, &l.w1, &l.b1, &l.w2, &l.b2};
@@ -763,7 +782,6 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
   embed_ln_kernel<768><<<(R + 7) / 8, 256, 0, st>>>(tokens, 1, h->words_f32.as<float>(), h->positions.as<float>(),
                                                    h->lnemb_g.as<float>(), h->lnemb_b.as<float>(), xd, hd, R, 0, state, h->V);
   CKL(h, "embed_ln_kernel");
-  const size_t attn_smem = static_cast<size_t>(beam) * (h->cur_M + h->T_alloc) * sizeof(float);
   for (int j = 0; j < nl; ++j) {
     DecLayer& l = h->dec[j];
     TRY(launch_gemm(h, gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, l.bqkv.as<float>(), ACT_NONE, qkv, 3 * D, false, 1, skip), st));
@@ -773,8 +791,8 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
     ap.src_row = src_row; ap.ctx = ctx; ap.B = h->cur_B; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
     ap.state = state;
     dim3 grid(h->cfg.dec_heads, h->cur_B);
-    if (beam == 1) decode_attn_kernel<1><<<grid, 128, attn_smem, st>>>(ap);
-    else if (beam == 4) decode_attn_kernel<4><<<grid, 128, attn_smem, st>>>(ap);
+    if (beam == 1) decode_attn_kernel<1><<<grid, 128, 0, st>>>(ap);
+    else if (beam == 4) decode_attn_kernel<4><<<grid, 128, 0, st>>>(ap);
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
     CKL(h, "decode_attn_kernel");
     TRY(launch_gemm(h, gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 2, skip), st));
@@ -797,12 +815,7 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
 }
 
 static int set_attn_smem_limit(gitb200_engine* h) {
-  const size_t need = static_cast<size_t>(h->cur_beam) * (h->cur_M + h->T_alloc) * sizeof(float);
-  if (need > 200 * 1024) return fail(h, "decode attention: sequence too long for the score buffer (%zu bytes)", need);
-  if (need > 40 * 1024) {
-    CK(cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need)));
-    CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need)));
-  }
+  (void)h;  // the single-pass decode attention keeps no per-key scores in shared memory
   return 0;
 }
 

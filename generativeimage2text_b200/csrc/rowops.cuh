@@ -261,12 +261,21 @@ struct SelectParams {
   const long long* forced;  // [rows, max_steps] or null
   StepState* state;
   float* step_logits;       // optional dump [steps, rows, V]
+  // per-row partial results of the vocabulary slices (grid.x = n_split CTAs per row)
+  int n_split;
+  float* part_max;          // [rows, n_split]
+  float* part_sum;          // [rows, n_split]  sum exp(v - part_max)
+  int* part_arg;            // [rows, n_split]
+  unsigned int* row_ticket; // [rows]
 };
 
+// grid (n_split, rows): each CTA folds one vocabulary slice of one row into (max, argmax, sum exp) with a
+// single online pass; the last CTA of a row combines the slices and does the reference's bookkeeping.
 __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p) {
   StepState* st = p.state;
   if (st->finished) return;
-  const int row = blockIdx.x;
+  const int row = blockIdx.y;
+  const int split = blockIdx.x;
   const int tid = threadIdx.x;
   const int step = st->step;
   const int cur_len = st->cur_len;
@@ -275,86 +284,118 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
   // masks are functions of the *input* sequence (predictions_so_far[:, -1]).
   const long long last = p.next_token[row];
   const bool first = (step == 0);
-  const bool row_done = (!first) && (last == p.eos);
+  const int chunk = (p.V + p.n_split - 1) / p.n_split;
+  const int lo = split * chunk;
+  const int hi = min(p.V, lo + chunk);
   if (p.step_logits != nullptr) {
     float* dst = p.step_logits + (static_cast<long long>(step) * p.rows + row) * p.V;
-    for (int i = tid; i < p.V; i += blockDim.x) dst[i] = z[i];
+    for (int i = lo + tid; i < hi; i += 256) dst[i] = z[i];
   }
-  __shared__ float s_val[256];
-  __shared__ int s_idx[256];
-  __shared__ float s_sum[256];
-  float best = -INFINITY;
-  int best_i = 0x7fffffff;
-  for (int i = tid; i < p.V; i += blockDim.x) {
-    float v = z[i];
-    if (!first && i == static_cast<int>(last)) v = -10000.0f;
-    if (v > best) {  // strided scan visits increasing i per thread -> keeps the lowest index on ties
-      best = v;
-      best_i = i;
+  float m = -INFINITY, ssum = 0.f;
+  int arg = 0x7fffffff;
+  for (int i0 = lo + tid; i0 < hi; i0 += 4 * 256) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      v[u] = (i < hi) ? z[i] : -INFINITY;
+      if (!first && i == static_cast<int>(last)) v[u] = -10000.0f;   // no-repeat (reference :330)
     }
-  }
-  s_val[tid] = best;
-  s_idx[tid] = best_i;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) {
-      const float ov = s_val[tid + o];
-      const int oi = s_idx[tid + o];
-      if (ov > s_val[tid] || (ov == s_val[tid] && oi < s_idx[tid])) {
-        s_val[tid] = ov;
-        s_idx[tid] = oi;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (v[u] > m) {   // increasing i per thread: keeps the lowest index on exact ties
+        ssum = ssum * __expf(m - v[u]) + 1.0f;
+        m = v[u];
+        arg = i;
+      } else if (v[u] != -INFINITY) {
+        ssum += __expf(v[u] - m);
       }
     }
-    __syncthreads();
   }
-  const float mx = s_val[0];
-  const int arg = s_idx[0];
-  float sum = 0.f;
-  for (int i = tid; i < p.V; i += blockDim.x) {
-    float v = z[i];
-    if (!first && i == static_cast<int>(last)) v = -10000.0f;
-    sum += __expf(v - mx);
+  // block reduce of (m, arg, ssum)
+  __shared__ float s_m[8], s_s[8];
+  __shared__ int s_a[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s_o = __shfl_xor_sync(0xffffffffu, ssum, o);
+    const int a_o = __shfl_xor_sync(0xffffffffu, arg, o);
+    const float mn = fmaxf(m, m_o);
+    const float sa = (m == -INFINITY) ? 0.f : __expf(m - mn);
+    const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - mn);
+    ssum = ssum * sa + s_o * sb;
+    if (m_o > m || (m_o == m && a_o < arg)) arg = a_o;
+    m = mn;
   }
-  s_sum[tid] = sum;
+  if ((tid & 31) == 0) { s_m[tid >> 5] = m; s_s[tid >> 5] = ssum; s_a[tid >> 5] = arg; }
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) s_sum[tid] += s_sum[tid + o];
-    __syncthreads();
-  }
   if (tid == 0) {
-    long long tok;
-    float lp;
-    if (row_done) {  // one-hot EOS distribution: log_softmax gives exactly 0 at EOS
-      tok = p.eos;
-      lp = 0.f;
-    } else {
-      tok = arg;
-      lp = -logf(s_sum[0]);  // z[arg] - mx - log(sum) with z[arg] == mx
+    for (int w = 1; w < 8; ++w) {
+      const float mn = fmaxf(m, s_m[w]);
+      const float sa = (m == -INFINITY) ? 0.f : __expf(m - mn);
+      const float sb = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - mn);
+      ssum = ssum * sa + s_s[w] * sb;
+      if (s_m[w] > m || (s_m[w] == m && s_a[w] < arg)) arg = s_a[w];
+      m = mn;
     }
-    p.tokens_out[static_cast<long long>(row) * p.max_steps + cur_len] = tok;
-    p.logprob_sum[row] += lp;
-    long long nxt = tok;
-    if (p.forced != nullptr) nxt = p.forced[static_cast<long long>(row) * p.max_steps + cur_len];
-    p.next_token[row] = nxt;
-    // reference checks `(last_predictions == eos).all()` on the sequence it feeds next
-    if (nxt != p.eos) atomicAdd(&st->not_eos, 1);
+    p.part_max[row * p.n_split + split] = m;
+    p.part_sum[row * p.n_split + split] = ssum;
+    p.part_arg[row * p.n_split + split] = arg;
     __threadfence();
-    const unsigned int t = atomicAdd(&st->ticket, 1u);
-    if (t == static_cast<unsigned int>(p.rows) - 1) {  // last row of this step: advance the loop state
+    const unsigned int t = atomicAdd(&p.row_ticket[row], 1u);
+    if (t == static_cast<unsigned int>(p.n_split) - 1) {
       __threadfence();
-      const int not_eos = atomicAdd(&st->not_eos, 0);
-      st->ticket = 0;
-      st->not_eos = 0;
-      st->cur_len = cur_len + 1;
-      st->final_len = cur_len + 1;
-      st->pos = st->pos + 1;
-      st->step = step + 1;
-      if (not_eos == 0) {
-        st->finished = 1;
-        if (first) st->empty_caption = 1;
+      p.row_ticket[row] = 0;
+      // combine the slices (slice order = index order, so ">" keeps the lowest index on ties)
+      float gm = -INFINITY, gs = 0.f;
+      int ga = 0;
+      for (int k = 0; k < p.n_split; ++k) {
+        const float pm = __ldcg(&p.part_max[row * p.n_split + k]);
+        const float ps = __ldcg(&p.part_sum[row * p.n_split + k]);
+        const int pa = __ldcg(&p.part_arg[row * p.n_split + k]);
+        const float mn = fmaxf(gm, pm);
+        const float sa = (gm == -INFINITY) ? 0.f : __expf(gm - mn);
+        const float sb = (pm == -INFINITY) ? 0.f : __expf(pm - mn);
+        gs = gs * sa + ps * sb;
+        if (pm > gm) ga = pa;
+        gm = mn;
       }
-      if (cur_len + 1 >= p.max_steps) st->finished = 1;
+      const bool row_done = (!first) && (last == p.eos);
+      long long tok;
+      float lp;
+      if (row_done) {  // one-hot EOS distribution (reference :347-351): log_softmax gives exactly 0 at EOS
+        tok = p.eos;
+        lp = 0.f;
+      } else {
+        tok = ga;
+        lp = -logf(gs);  // z[arg] - max - log(sum exp(z - max)) with z[arg] == max
+      }
+      p.tokens_out[static_cast<long long>(row) * p.max_steps + cur_len] = tok;
+      p.logprob_sum[row] += lp;
+      long long nxt = tok;
+      if (p.forced != nullptr) nxt = p.forced[static_cast<long long>(row) * p.max_steps + cur_len];
+      p.next_token[row] = nxt;
+      // reference checks `(last_predictions == eos).all()` on the sequence it feeds next
+      if (nxt != p.eos) atomicAdd(&st->not_eos, 1);
       __threadfence();
+      const unsigned int tr = atomicAdd(&st->ticket, 1u);
+      if (tr == static_cast<unsigned int>(p.rows) - 1) {  // last row of this step: advance the loop state
+        __threadfence();
+        const int not_eos = atomicAdd(&st->not_eos, 0);
+        st->ticket = 0;
+        st->not_eos = 0;
+        st->cur_len = cur_len + 1;
+        st->final_len = cur_len + 1;
+        st->pos = st->pos + 1;
+        st->step = step + 1;
+        if (not_eos == 0) {
+          st->finished = 1;
+          if (first) st->empty_caption = 1;
+        }
+        if (cur_len + 1 >= p.max_steps) st->finished = 1;
+        __threadfence();
+      }
     }
   }
 }

