@@ -42,6 +42,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int32), c_void_p]),
     'gitb200_launch_count': (c_int64, [c_void_p]),
     'gitb200_set_option': (c_int, [c_void_p, c_char_p, c_int64]),
+    'gitb200_debug_timeline': (c_int, [c_int, c_void_p, c_int]),
     'gitb200_op_gemm': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
     'gitb200_op_layernorm': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,

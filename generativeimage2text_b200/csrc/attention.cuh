@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(NW * 32) flash_attn_kernel(const AttnParams p)
 
 // ------------------------------------------------------------------------------------------------
 struct DecAttnParams {
-  const float* qkv;                // [R, 3*D] fp32, bias included (q | k | v)
+  float* qkv;                      // [R, 3*D] fp32 (q | k | v): split-K accumulation buffer, zeroed after reading
+  const float* bqkv;               // [3*D] bias, added here
   const __nv_bfloat16* img_k;      // [B, M, D]
   const __nv_bfloat16* img_v;
   __nv_bfloat16* txt_k;            // [R, T_alloc, D]
@@ -226,6 +227,9 @@ __device__ __forceinline__ void dec_attn_update(float (&sc)[4], const uint4 (&w)
 // folded into per-group online-softmax states that are merged at the end (flash-decoding style).
 template <int NQ>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p) {
+  griddep_launch();
+  griddep_wait();
+  tl_mark(3);
   if (p.state != nullptr && p.state->finished) return;
   const int pos = (p.state != nullptr) ? p.state->pos : p.pos_fixed;
   const int n_txt = pos + 1;
@@ -242,13 +246,17 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
   // ---- q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V (bf16) ----
   for (int qi = 0; qi < NQ; ++qi) {
     const int r = b * NQ + qi;
-    const float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
+    float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
+    const float* bias = p.bqkv + h * 64;
     if (tid < 64) {
-      q_s[qi][tid] = row[tid] * 0.125f;
-      p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(row[D + tid]);
+      q_s[qi][tid] = (row[tid] + bias[tid]) * 0.125f;
+      p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(row[D + tid] + bias[D + tid]);
+      row[tid] = 0.f;
+      row[D + tid] = 0.f;
     } else {
       const int d = tid - 64;
-      p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(row[2 * D + d]);
+      p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(row[2 * D + d] + bias[2 * D + d]);
+      row[2 * D + d] = 0.f;
     }
   }
   __syncthreads();

@@ -37,6 +37,7 @@ struct GemmParams {
   int row_offset;
   const int* skip;            // device flag: non-zero -> the whole launch is a no-op (finished decode)
   unsigned long long* dbg;    // optional [8] %globaltimer stamps of CTA 0 (profiling aid; null in production)
+  int pdl;                    // launched with programmatic dependent launch: prefetch weights, then griddep_wait()
 };
 
 template <int BN>
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmParams p) {
   using C = GemmCfg<BN>;
-  if (p.skip != nullptr && *p.skip != 0) return;  // uniform over the grid
+  if (p.pdl) griddep_launch();
+  if (!p.pdl && p.skip != nullptr && *p.skip != 0) return;  // uniform over the grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -107,6 +109,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();
+  // PDL: everything above overlapped the predecessor kernel. The producer additionally prefetches the weight
+  // tiles (which no kernel writes) before it waits; every other thread waits here.
+  if (p.pdl && !(warp == 0 && lane == 0)) griddep_wait();
+  if (p.pdl) tl_mark(1000 + static_cast<int>(gridDim.x));
 
   const int m_tiles = (p.M + C::BM - 1) / C::BM;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -120,6 +126,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int npre = 0;  // k-blocks of the first tile whose weight tile was requested before griddep_wait()
+      if (p.pdl) {
+        if (p.transposed && static_cast<int>(blockIdx.x) < num_tiles) {
+          const int tile = blockIdx.x;
+          const int split = tile / mn_tiles;
+          const int rem = tile - split * mn_tiles;
+          const int m_blk = rem / n_tiles;
+          const int kb0 = split * kb_per;
+          const int kb1 = min(kb_total, kb0 + kb_per);
+          npre = min(C::STAGES, kb1 - kb0);
+          for (int i = 0; i < npre; ++i) {
+            mbar_arrive_expect_tx(&full[i], C::STAGE_BYTES);
+            tma_load_2d(sA + i * C::A_BYTES, &tmA, &full[i], (kb0 + i) * C::BK, m_blk * C::BM);
+          }
+        }
+        griddep_wait();
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / mn_tiles;
         const int rem = tile - split * mn_tiles;
@@ -128,10 +151,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int kb0 = split * kb_per;
         const int kb1 = min(kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-          tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full[stage], kb * C::BK, m_blk * C::BM);
-          tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full[stage], kb * C::BK, n_blk * BN);
+          if (npre > 0) {  // weight tile already in flight: add the (dependent) activation tile
+            --npre;
+            tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full[stage], kb * C::BK, n_blk * BN);
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+            tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full[stage], kb * C::BK, m_blk * C::BM);
+            tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full[stage], kb * C::BK, n_blk * BN);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -184,6 +212,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // staging buffer so that global loads (residual) and stores are fully coalesced 128-byte rows.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
+    const bool store_ok = !(p.pdl && p.skip != nullptr && *p.skip != 0);  // finished decode: compute, do not store
     uint8_t* stg = sStage + (warp - 4) * (32 * 128);
     const uint32_t stg_u32 = smem_u32(stg);
     int accum = 0;
@@ -208,10 +237,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t addr = stg_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]),
-                         "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                         : "memory");
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           }
           __syncwarp();
           // phase 2: 8 lanes per row (4 columns each), 4 rows per instruction
@@ -221,35 +248,48 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + c4);
           const int seg = n0 / p.seg_n;
           const int nn = n0 - seg * p.seg_n + c4 * 4;
+          float4 v[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rsub;
-            const int row = row0 + rr;
-            float4 v;
-            const uint32_t addr = stg_u32 + rr * 128 + ((c4 ^ (rr & 7)) << 4);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if (p.act != ACT_NONE) {
-              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-            }
-            if (row < p.M) {
-              if (p.resid != nullptr) {
+            v[it] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+          }
+          if (p.resid != nullptr) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = row0 + it * 4 + rsub;
+              if (row < p.M) {
                 const float4 r4 = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ld_resid + n0 + c4 * 4);
-                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-              }
-              const int b = row / p.rows_per_batch;
-              const int s = row - b * p.rows_per_batch;
-              const long long orow = static_cast<long long>(b) * p.batch_stride[seg] + s + p.row_offset;
-              if (p.out_bf16) {
-                uint2 o;
-                o.x = pack_bf16(v.x, v.y);
-                o.y = pack_bf16(v.z, v.w);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + orow * p.ldo[seg] + nn) = o;
-              } else {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + orow * p.ldo[seg] + nn) = v;
+                v[it].x += r4.x; v[it].y += r4.y; v[it].z += r4.z; v[it].w += r4.w;
               }
             }
+          }
+          // row map of the first row of this lane; later rows advance by 4 and wrap at the batch boundary
+          int bq = (row0 + rsub) / p.rows_per_batch;
+          int sq = (row0 + rsub) - bq * p.rows_per_batch;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = row0 + it * 4 + rsub;
+            float4 o = v[it];
+            // bias and activation come before the residual in every caller that uses both (resid => act none)
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (p.act != ACT_NONE) {
+              o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
+              o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
+            }
+            if (row < p.M && store_ok) {
+              const long long orow = static_cast<long long>(bq) * p.batch_stride[seg] + sq + p.row_offset;
+              if (p.out_bf16) {
+                uint2 pk;
+                pk.x = pack_bf16(o.x, o.y);
+                pk.y = pack_bf16(o.z, o.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + orow * p.ldo[seg] + nn) = pk;
+              } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + orow * p.ldo[seg] + nn) = o;
+              }
+            }
+            sq += 4;
+            while (sq >= p.rows_per_batch) { sq -= p.rows_per_batch; ++bq; }
           }
           __syncwarp();
         } else {
@@ -257,7 +297,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int row = row0 + lane;
           const bool row_ok = row < p.M;
           const float bv = (p.bias != nullptr && row_ok && split == 0) ? __ldg(p.bias + row) : 0.0f;
-          if (row_ok) {
+          if (row_ok && store_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int rr = n0 + j;

@@ -22,6 +22,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/gitb200.h"
@@ -93,6 +94,7 @@ struct gitb200_engine {
   std::string err;
   int64_t launches = 0;
   bool use_graph = true;
+  bool use_pdl = true;
 
   // derived geometry
   int g = 0, L = 0, Kpatch = 0, Kp = 0, d = 0, D = 0, F = 0, V = 0;
@@ -152,6 +154,24 @@ static int fail(gitb200_engine* h, const char* fmt, ...) {
     int rc_ = (expr);             \
     if (rc_ != 0) return rc_;     \
   } while (0)
+
+// Kernel launch with optional programmatic dependent launch (the decode step chains ~45 small kernels; PDL lets
+// each one's prologue / weight prefetch overlap its predecessor's tail, also inside a captured CUDA graph).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // TMA descriptors
@@ -222,7 +242,7 @@ static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st)
   const int n_tiles = (c.p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles * c.p.k_splits;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-  gemm_bf16_tcgen05<BN><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, c.p);
+  CK(launch_k(c.p.pdl != 0, gemm_bf16_tcgen05<BN>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
   CKL(h, "gemm_bf16_tcgen05");
   return 0;
 }
@@ -290,7 +310,7 @@ static GemmCall gemm_plain(const bf16* A, long long lda, const bf16* W, long lon
 // Skinny decode-step GEMM: out[r][f] = sum_k X[r][k] W[f][k] (+bias[f]) (+act) -- swap-AB, transposed epilogue.
 static GemmCall gemm_skinny(const bf16* X, long long ldx, const bf16* W, long long ldw, int rows, int feats, int K,
                             const float* bias, int act, void* out, long long ldo, bool out_bf16, int k_splits,
-                            const int* skip) {
+                            const int* skip, bool pdl = false) {
   GemmCall c;
   c.A = W; c.lda = ldw; c.B = X; c.ldb = ldx;
   c.p.M = feats; c.p.N = rows; c.p.K = K; c.p.k_splits = k_splits;
@@ -298,16 +318,17 @@ static GemmCall gemm_skinny(const bf16* X, long long ldx, const bf16* W, long lo
   c.p.bias = bias; c.p.act = act;
   c.p.out[0] = out; c.p.ldo[0] = ldo; c.p.out_bf16 = out_bf16 ? 1 : 0;
   c.p.skip = skip;
+  c.p.pdl = pdl ? 1 : 0;
   return c;
 }
 
 // ------------------------------------------------------------------------------------------------
 // other launch helpers
 // ------------------------------------------------------------------------------------------------
-static int launch_ln(gitb200_engine* h, const LnParams& p, int D, cudaStream_t st) {
+static int launch_ln(gitb200_engine* h, const LnParams& p, int D, cudaStream_t st, bool pdl = false) {
   const int grid = (p.rows + 7) / 8;
-  if (D == 768) layernorm_kernel<768><<<grid, 256, 0, st>>>(p);
-  else if (D == 1024) layernorm_kernel<1024><<<grid, 256, 0, st>>>(p);
+  if (D == 768) CK(launch_k(pdl, layernorm_kernel<768>, dim3(grid), dim3(256), 0, st, p));
+  else if (D == 1024) CK(launch_k(pdl, layernorm_kernel<1024>, dim3(grid), dim3(256), 0, st, p));
   else return fail(h, "layernorm: unsupported width %d", D);
   CKL(h, "layernorm_kernel");
   return 0;
@@ -386,6 +407,7 @@ extern "C" int64_t gitb200_launch_count(const gitb200_engine* h) { return h ? h-
 extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value) {
   if (!h || !name) return 1;
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
+  if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   return fail(h, "unknown option %s", name);
 }
 
@@ -735,6 +757,7 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
   bf16* u = h->pu.as<bf16>();
   // split-K accumulation buffer of the decode step must start at zero
   CK(cudaMemsetAsync(h->t_t.p, 0, static_cast<size_t>(R) * D * 4, st));
+  CK(cudaMemsetAsync(h->qkv_t.p, 0, static_cast<size_t>(R) * 3 * D * 4, st));
 
   // visual projection: Linear(dv -> 768) + LayerNorm(1e-5)
   TRY(launch_gemm(h, gemm_plain(h->feats.as<bf16>(), d, h->w_vp.as<bf16>(), d, static_cast<int>(rows), D, d, h->b_vp.as<float>(), ACT_NONE, nullptr, t, false), st));
@@ -779,38 +802,43 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
   bf16* ctx = h->ctx_t.as<bf16>();
   float* t = h->t_t.as<float>();
   bf16* u = h->u_t.as<bf16>();
-  embed_ln_kernel<768><<<(R + 7) / 8, 256, 0, st>>>(tokens, 1, h->words_f32.as<float>(), h->positions.as<float>(),
-                                                   h->lnemb_g.as<float>(), h->lnemb_b.as<float>(), xd, hd, R, 0, state, h->V);
+  const bool pdl = h->use_pdl;
+  CK(launch_k(pdl, embed_ln_kernel<768>, dim3((R + 7) / 8), dim3(256), 0, st, tokens, 1LL, h->words_f32.as<float>(),
+              h->positions.as<float>(), h->lnemb_g.as<float>(), h->lnemb_b.as<float>(), xd, hd, R, 0,
+              static_cast<const StepState*>(state), h->V));
   CKL(h, "embed_ln_kernel");
+  // Split-K factors: a handful of activation rows against [features, K] weights is latency bound, so the K
+  // dimension is spread over enough CTAs that each one has all of its weight tiles in flight at once
+  // (partials meet in fp32 atomics; bias / residual / LayerNorm live in the consumer kernel).
   for (int j = 0; j < nl; ++j) {
     DecLayer& l = h->dec[j];
-    TRY(launch_gemm(h, gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, l.bqkv.as<float>(), ACT_NONE, qkv, 3 * D, false, 1, skip), st));
+    TRY(launch_gemm(h, gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, nullptr, ACT_NONE, qkv, 3 * D, false, 3, skip, pdl), st));
     DecAttnParams ap{};
-    ap.qkv = qkv; ap.img_k = img_kv_ptr(h, j, 0); ap.img_v = img_kv_ptr(h, j, 1);
+    ap.qkv = qkv; ap.bqkv = l.bqkv.as<float>(); ap.img_k = img_kv_ptr(h, j, 0); ap.img_v = img_kv_ptr(h, j, 1);
     ap.txt_k = txt_kv_ptr(h, j, 0); ap.txt_v = txt_kv_ptr(h, j, 1);
     ap.src_row = src_row; ap.ctx = ctx; ap.B = h->cur_B; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
     ap.state = state;
     dim3 grid(h->cfg.dec_heads, h->cur_B);
-    if (beam == 1) decode_attn_kernel<1><<<grid, 128, 0, st>>>(ap);
-    else if (beam == 4) decode_attn_kernel<4><<<grid, 128, 0, st>>>(ap);
+    if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), 0, st, ap));
+    else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), 0, st, ap));
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
     CKL(h, "decode_attn_kernel");
-    TRY(launch_gemm(h, gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 2, skip), st));
+    TRY(launch_gemm(h, gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 6, skip, pdl), st));
     {
       LnParams p = ln_params(t, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, R);
       p.zero_x = 1; p.skip_flag = skip;
-      TRY(launch_ln(h, p, D, st));
+      TRY(launch_ln(h, p, D, st, pdl));
     }
-    TRY(launch_gemm(h, gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip), st));
-    TRY(launch_gemm(h, gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, 4, skip), st));
+    TRY(launch_gemm(h, gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip, pdl), st));
+    TRY(launch_gemm(h, gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, 12, skip, pdl), st));
     {
       LnParams p = ln_params(t, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, R);
       p.zero_x = 1; p.skip_flag = skip;
-      TRY(launch_ln(h, p, D, st));
+      TRY(launch_ln(h, p, D, st, pdl));
     }
   }
   if (lm_head)
-    TRY(launch_gemm(h, gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, h->logits.p, h->V, false, 1, skip), st));
+    TRY(launch_gemm(h, gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, h->logits.p, h->V, false, 1, skip, pdl), st));
   return 0;
 }
 

@@ -20,6 +20,27 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// Optional in-situ timeline (debug): when enabled, block 0 / thread 0 of every decode-step kernel appends
+// (%globaltimer, kernel id) right after its dependency wait, i.e. when its predecessor has fully completed.
+__device__ unsigned long long* g_tl_buf = nullptr;
+__device__ unsigned int g_tl_count = 0;
+constexpr unsigned int kTimelineMax = 8192;
+__device__ __forceinline__ void tl_mark(int kid) {
+  if (g_tl_buf != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    const unsigned int i = atomicAdd(&g_tl_count, 1u);
+    if (i < kTimelineMax) {
+      g_tl_buf[2 * i] = globaltimer_ns();
+      g_tl_buf[2 * i + 1] = static_cast<unsigned long long>(kid);
+    }
+  }
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor is still running; griddep_wait() blocks until the predecessor grid has completed
+// and its writes are visible, griddep_launch() lets the successor's prologue begin. Both are no-ops otherwise.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------

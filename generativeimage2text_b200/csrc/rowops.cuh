@@ -41,6 +41,9 @@ template <int D>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   static_assert(D % 128 == 0, "D");
   constexpr int NV = D / 128;
+  griddep_launch();
+  griddep_wait();
+  tl_mark(2);
   if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -202,6 +205,9 @@ embed_ln_kernel(const long long* __restrict__ tokens, long long tok_stride, cons
                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int rows, int pos_base,
                 const StepState* __restrict__ state, int vocab) {
   constexpr int NV = D / 128;
+  griddep_launch();
+  griddep_wait();
+  tl_mark(4);
   if (state != nullptr && state->finished) return;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -272,6 +278,9 @@ struct SelectParams {
 // grid (n_split, rows): each CTA folds one vocabulary slice of one row into (max, argmax, sum exp) with a
 // single online pass; the last CTA of a row combines the slices and does the reference's bookkeeping.
 __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p) {
+  griddep_launch();
+  griddep_wait();
+  tl_mark(5);
   StepState* st = p.state;
   if (st->finished) return;
   const int row = blockIdx.y;

@@ -66,6 +66,8 @@ __device__ __forceinline__ float beam_length_norm(int length, float lp) {
 
 // One CTA per row: lse = logsumexp(z), then the row's top-NC values of (z - lse + beam_score[row]).
 __global__ void __launch_bounds__(256) beam_row_topk_kernel(const BeamParams p) {
+  griddep_launch();
+  griddep_wait();
   StepState* st = p.state;
   if (st->finished) return;
   const int row = blockIdx.x;
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const BeamParams p) 
 
 // One thread block per image (32 threads; the bookkeeping itself is sequential like the reference's loop).
 __global__ void __launch_bounds__(32) beam_update_kernel(const BeamParams p) {
+  griddep_launch();
+  griddep_wait();
   StepState* st = p.state;
   if (st->finished) return;
   const int b = blockIdx.x;

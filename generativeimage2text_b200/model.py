@@ -139,6 +139,11 @@ class GitB200CaptioningModel(nn.Module):
             h = ctypes.c_void_p()
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
             self._engine, self._engine_device, self._weights_sig = h, dev, None
+            import os
+            for opt in ('use_graph', 'use_pdl'):     # debugging switches: GITB200_USE_GRAPH=0 / GITB200_USE_PDL=0
+                v = os.environ.get('GITB200_' + opt.upper())
+                if v is not None:
+                    _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')
         sig = self._weights_signature()
         if sig != self._weights_sig:
             for key, p in self.state_dict(keep_vars=True).items():

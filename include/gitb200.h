@@ -141,6 +141,10 @@ int gitb200_op_attention(const void* q_dev, const void* k_dev, const void* v_dev
                          long long kv_batch_stride, long long out_row_stride, long long out_batch_stride,
                          void* stream);
 
+/* Debug aid: in-situ timeline of the decode-step kernels. enable != 0 arms it; enable == 0 copies up to
+ * max_entries (globaltimer ns, kernel id) pairs to out_host, disarms, and returns the number of entries. */
+int gitb200_debug_timeline(int enable, unsigned long long* out_host, int max_entries);
+
 #ifdef __cplusplus
 }
 #endif
