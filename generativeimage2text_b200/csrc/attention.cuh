@@ -192,6 +192,9 @@ struct DecAttnParams {
   int B, M, T_alloc, D;
   const StepState* state;          // text position = state->pos (or pos_fixed when null)
   int pos_fixed;
+  int chunk_rows;                  // image keys staged per TMA round (<= 512), box_rows * n_boxes
+  int box_rows;                    // rows per TMA box (<= 256)
+  ChainSync chain;
 };
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
@@ -222,17 +225,19 @@ __device__ __forceinline__ void dec_attn_update(float (&sc)[4], const uint4 (&w)
   m = m_new;
 }
 
-// grid (heads, images); 128 threads = 16 key groups x 8 lanes (8 head dims each, 128-bit loads).
-// Single pass: K and V rows of a key block are requested together (8 x 16 B in flight per thread), scores are
-// folded into per-group online-softmax states that are merged at the end (flash-decoding style).
+// grid (heads, images); 128 threads = 16 key groups x 8 lanes (8 head dims each, 128-bit accesses).
+// The image K/V slice of this (image, head) -- M rows of 128 bytes, constant during decoding -- is fetched by
+// TMA into shared memory BEFORE the dependency wait, so under programmatic dependent launch the HBM stream of
+// this kernel overlaps the QKV GEMM that precedes it; after the wait only the new token's q/k/v, the short
+// text history and the arithmetic remain.  Scores are folded into per-group online-softmax states that are
+// merged at the end (flash-decoding style), single pass over K and V.
 template <int NQ>
-__global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p) {
-  griddep_launch();
-  griddep_wait();
-  tl_mark(3);
-  if (p.state != nullptr && p.state->finished) return;
-  const int pos = (p.state != nullptr) ? p.state->pos : p.pos_fixed;
-  const int n_txt = pos + 1;
+__global__ void __launch_bounds__(128)
+decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const DecAttnParams p) {
+  extern __shared__ uint8_t attn_dyn[];
+  uint8_t* sK = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_dyn) + 127) & ~uintptr_t(127));
+  uint8_t* sV = sK + static_cast<size_t>(p.chunk_rows) * 128;
+  __shared__ uint64_t bar;
   __shared__ float q_s[NQ][64];
   __shared__ float red_m[4][NQ];
   __shared__ float red_l[4][NQ];
@@ -242,6 +247,45 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int D = p.D;
+  const int n_chunks = (p.M + p.chunk_rows - 1) / p.chunk_rows;
+
+  griddep_launch();
+  tl_mark(100003);
+  if (tid == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue_chunk = [&](int c) {  // one thread
+    const int rows_c = min(p.chunk_rows, p.M - c * p.chunk_rows);
+    const int nb = (rows_c + p.box_rows - 1) / p.box_rows;
+    mbar_arrive_expect_tx(&bar, static_cast<uint32_t>(2 * nb * p.box_rows * 128));
+    for (int i = 0; i < nb; ++i) {
+      const int grow = b * p.M + c * p.chunk_rows + i * p.box_rows;
+      tma_load_2d(sK + static_cast<size_t>(i) * p.box_rows * 128, &tmK, &bar, h * 64, grow);
+      tma_load_2d(sV + static_cast<size_t>(i) * p.box_rows * 128, &tmV, &bar, h * 64, grow);
+    }
+  };
+  if (tid == 0) issue_chunk(0);
+  if (p.chain.counters != nullptr) {
+    // `finished` only changes between steps (full dependency): in a finished step no kernel waits or signals
+    if (p.state != nullptr && p.state->finished) {
+      mbar_wait(&bar, 0);  // never leave with a bulk copy in flight into this CTA's shared memory
+      return;
+    }
+    chain_wait(p.chain);
+  } else {
+    griddep_wait();
+    if (p.state != nullptr && p.state->finished) {
+      mbar_wait(&bar, 0);
+      return;
+    }
+  }
+  tl_mark(3);
+  const int pos = (p.state != nullptr) ? p.state->pos : p.pos_fixed;
+  const int n_txt = pos + 1;
 
   // ---- q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V (bf16) ----
   for (int qi = 0; qi < NQ; ++qi) {
@@ -249,13 +293,13 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
     float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
     const float* bias = p.bqkv + h * 64;
     if (tid < 64) {
-      q_s[qi][tid] = (row[tid] + bias[tid]) * 0.125f;
-      p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(row[D + tid] + bias[D + tid]);
+      q_s[qi][tid] = (__ldcg(row + tid) + bias[tid]) * 0.125f;
+      p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(__ldcg(row + D + tid) + bias[D + tid]);
       row[tid] = 0.f;
       row[D + tid] = 0.f;
     } else {
       const int d = tid - 64;
-      p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(row[2 * D + d] + bias[2 * D + d]);
+      p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(__ldcg(row + 2 * D + d) + bias[2 * D + d]);
       row[2 * D + d] = 0.f;
     }
   }
@@ -276,40 +320,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
     }
   }
 
-  // ---- image keys: shared by the NQ beams of this image ----
-  {
-    const __nv_bfloat16* kb = p.img_k + static_cast<long long>(b) * p.M * D + h * 64 + gl * 8;
-    const __nv_bfloat16* vb = p.img_v + static_cast<long long>(b) * p.M * D + h * 64 + gl * 8;
-    for (int base = 0; base < p.M; base += 64) {  // uniform trip count: the shuffles below stay converged
-      uint4 u[4], w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int s = base + grp + 16 * i;
-        const bool ok = s < p.M;
-        u[i] = ok ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
-        w[i] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(s) * D)) : make_uint4(0, 0, 0, 0);
-      }
-      float kf[4][8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) bf16x8_to_f32(u[i], kf[i]);
-#pragma unroll
-      for (int qi = 0; qi < NQ; ++qi) {
-        float sc[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a = 0.f;
-#pragma unroll
-          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[i][d], a);
-          a += __shfl_xor_sync(0xffffffffu, a, 1);
-          a += __shfl_xor_sync(0xffffffffu, a, 2);
-          a += __shfl_xor_sync(0xffffffffu, a, 4);
-          sc[i] = (base + grp + 16 * i < p.M) ? a : -INFINITY;
-        }
-        dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
-      }
-    }
-  }
-  // ---- text keys: each beam row has its own history (through the src_row indirection) ----
+  // ---- text keys first (global loads; the TMA of the image slice is still landing) ----
+  // each beam row has its own history (through the src_row indirection)
 #pragma unroll
   for (int qi = 0; qi < NQ; ++qi) {
     const int r = b * NQ + qi;
@@ -342,6 +354,43 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
         sc[i] = (base + grp + 16 * i < n_txt) ? a : -INFINITY;
       }
       dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
+    }
+  }
+  // ---- image keys from shared memory: shared by the NQ beams of this image ----
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c > 0) {
+      __syncthreads();  // everyone is done with the previous chunk
+      if (tid == 0) issue_chunk(c);
+    }
+    mbar_wait(&bar, static_cast<uint32_t>(c & 1));
+    const int rows_c = min(p.chunk_rows, p.M - c * p.chunk_rows);
+    for (int base = 0; base < rows_c; base += 64) {  // uniform trip count: the shuffles below stay converged
+      uint4 u[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int s = base + grp + 16 * i;
+        const bool ok = s < rows_c;
+        u[i] = ok ? *reinterpret_cast<const uint4*>(sK + static_cast<size_t>(s) * 128 + gl * 16) : make_uint4(0, 0, 0, 0);
+        w[i] = ok ? *reinterpret_cast<const uint4*>(sV + static_cast<size_t>(s) * 128 + gl * 16) : make_uint4(0, 0, 0, 0);
+      }
+      float kf[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bf16x8_to_f32(u[i], kf[i]);
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+        float sc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[i][d], a);
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          a += __shfl_xor_sync(0xffffffffu, a, 4);
+          sc[i] = (base + grp + 16 * i < rows_c) ? a : -INFINITY;
+        }
+        dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
+      }
     }
   }
   // ---- merge the 16 group states: 4 groups of a warp by shuffles, the 4 warps through smem ----
@@ -384,6 +433,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
     }
     p.ctx[static_cast<long long>(b * NQ + qi) * D + h * 64 + d] = __float2bfloat16_rn(a / l);
   }
+  tl_mark(200003);
+  chain_signal(p.chain);
 }
 
 }  // namespace gitb200

@@ -38,6 +38,7 @@ struct GemmParams {
   const int* skip;            // device flag: non-zero -> the whole launch is a no-op (finished decode)
   unsigned long long* dbg;    // optional [8] %globaltimer stamps of CTA 0 (profiling aid; null in production)
   int pdl;                    // launched with programmatic dependent launch: prefetch weights, then griddep_wait()
+  ChainSync chain;            // flag-based ordering inside the decode step (see ptx.cuh); counters == null: off
 };
 
 template <int BN>
@@ -68,7 +69,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const GemmParams p) {
   using C = GemmCfg<BN>;
   if (p.pdl) griddep_launch();
-  if (!p.pdl && p.skip != nullptr && *p.skip != 0) return;  // uniform over the grid
+  if (p.pdl) tl_mark(100000 + 1000 + static_cast<int>(gridDim.x));
+  // `skip` (decode finished) only changes between steps, which are separated by full dependencies
+  if ((!p.pdl || p.chain.counters != nullptr) && p.skip != nullptr && *p.skip != 0) return;  // uniform over the grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -111,7 +114,27 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();
   // PDL: everything above overlapped the predecessor kernel. The producer additionally prefetches the weight
   // tiles (which no kernel writes) before it waits; every other thread waits here.
-  if (p.pdl && !(warp == 0 && lane == 0)) griddep_wait();
+  const bool chained = p.chain.counters != nullptr;
+  if (chained) {
+    // weights are never written during decoding: request the first tiles before waiting for the predecessor
+    if (warp == 0 && lane == 0 && p.transposed && static_cast<int>(blockIdx.x) < ((p.M + C::BM - 1) / C::BM) * ((p.N + BN - 1) / BN) * p.k_splits) {
+      const int mt = (p.M + C::BM - 1) / C::BM, nt = (p.N + BN - 1) / BN;
+      const int kbt = (p.K + C::BK - 1) / C::BK, kbp = (kbt + p.k_splits - 1) / p.k_splits;
+      const int tile = blockIdx.x;
+      const int split = tile / (mt * nt);
+      const int m_blk = (tile - split * mt * nt) / nt;
+      const int kb0 = split * kbp;
+      const int kb1 = min(kbt, kb0 + kbp);
+      const int npre = min(C::STAGES, kb1 - kb0);
+      for (int i = 0; i < npre; ++i) {
+        mbar_arrive_expect_tx(&full[i], C::STAGE_BYTES);
+        tma_load_2d(sA + i * C::A_BYTES, &tmA, &full[i], (kb0 + i) * C::BK, m_blk * C::BM);
+      }
+    }
+    chain_wait(p.chain);
+  } else if (p.pdl && !(warp == 0 && lane == 0)) {
+    griddep_wait();
+  }
   if (p.pdl) tl_mark(1000 + static_cast<int>(gridDim.x));
 
   const int m_tiles = (p.M + C::BM - 1) / C::BM;
@@ -126,8 +149,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int npre = 0;  // k-blocks of the first tile whose weight tile was requested before griddep_wait()
-      if (p.pdl) {
+      int npre = 0;  // k-blocks of the first tile whose weight tile was requested before the dependency wait
+      if (chained) {
+        if (p.transposed && static_cast<int>(blockIdx.x) < num_tiles) {
+          const int split = static_cast<int>(blockIdx.x) / mn_tiles;
+          const int kb0 = split * kb_per;
+          npre = min(C::STAGES, min(kb_total, kb0 + kb_per) - kb0);
+        }
+      } else if (p.pdl) {
         if (p.transposed && static_cast<int>(blockIdx.x) < num_tiles) {
           const int tile = blockIdx.x;
           const int split = tile / mn_tiles;
@@ -186,6 +215,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (dbg && tile == 0 && kb == kb0) p.dbg[2] = globaltimer_ns();
+          if (p.pdl && tile == static_cast<int>(blockIdx.x) && kb == kb0) tl_mark_one(300000 + 1000 + static_cast<int>(gridDim.x));
           const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
           const uint32_t b_base = smem_u32(sB + stage * C::B_BYTES);
 #pragma unroll
@@ -212,7 +242,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // staging buffer so that global loads (residual) and stores are fully coalesced 128-byte rows.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    const bool store_ok = !(p.pdl && p.skip != nullptr && *p.skip != 0);  // finished decode: compute, do not store
+    const bool store_ok = !(p.pdl && !chained && p.skip != nullptr && *p.skip != 0);  // finished decode: compute, do not store
     uint8_t* stg = sStage + (warp - 4) * (32 * 128);
     const uint32_t stg_u32 = smem_u32(stg);
     int accum = 0;
@@ -225,6 +255,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull[accum], accum_phase);
       tc_fence_after();
       if (dbg && tile == 0 && warp == 4 && lane == 0) p.dbg[4] = globaltimer_ns();
+      if (p.pdl && tile == static_cast<int>(blockIdx.x) && warp == 4 && lane == 0) tl_mark_one(400000 + 1000 + static_cast<int>(gridDim.x));
       const int row0 = m_blk * C::BM + q * 32;  // first row of this warp
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -293,28 +324,69 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           __syncwarp();
         } else {
-          // transposed: lane = output feature, register j = activation row n0 + j (stores coalesce over lanes)
-          const int row = row0 + lane;
-          const bool row_ok = row < p.M;
-          const float bv = (p.bias != nullptr && row_ok && split == 0) ? __ldg(p.bias + row) : 0.0f;
-          if (row_ok && store_ok) {
+          // transposed ("swap-AB"): lane = output feature, register j = activation row n0 + j.  Stage the 32x32
+          // chunk as [activation row][feature] so that each lane then owns 4 consecutive features of one row:
+          // 128-bit stores / vector reductions (a warp-wide scalar RED costs ~1.3 cycles per lane on the LSU).
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int rr = n0 + j;
-              if (rr < p.N) {
-                float v = __uint_as_float(r[j]) + bv;
-                v = apply_act(v, p.act);
-                const long long off = static_cast<long long>(rr) * p.ldo[0] + row;
-                if (p.atomic) {
-                  atomicAdd(reinterpret_cast<float*>(p.out[0]) + off, v);
-                } else if (p.out_bf16) {
-                  reinterpret_cast<__nv_bfloat16*>(p.out[0])[off] = __float2bfloat16_rn(v);
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<uint32_t*>(stg + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + ((lane & 3) << 2)) = r[j];
+          __syncwarp();
+          const int c4 = lane & 7;
+          const int rsub = lane >> 3;
+          const int f0 = row0 + c4 * 4;  // first of this lane's 4 features
+          const bool full4 = (f0 + 3) < p.M;
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias != nullptr && split == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (f0 + e < p.M) bv[e] = __ldg(p.bias + f0 + e);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const int arow = n0 + rr;
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+            float v[4] = {t4.x + bv[0], t4.y + bv[1], t4.z + bv[2], t4.w + bv[3]};
+            if (p.act != ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act);
+            }
+            if (arow < p.N && store_ok && f0 < p.M) {
+              const long long off = static_cast<long long>(arow) * p.ldo[0] + f0;
+              if (p.atomic) {
+                float* dst = reinterpret_cast<float*>(p.out[0]) + off;
+                if (full4) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
                 } else {
-                  reinterpret_cast<float*>(p.out[0])[off] = v;
+                  for (int e = 0; e < 4; ++e)
+                    if (f0 + e < p.M) atomicAdd(dst + e, v[e]);
+                }
+              } else if (p.out_bf16) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[0]) + off;
+                if (full4 && (p.ldo[0] & 3) == 0) {
+                  uint2 pk;
+                  pk.x = pack_bf16(v[0], v[1]);
+                  pk.y = pack_bf16(v[2], v[3]);
+                  *reinterpret_cast<uint2*>(dst) = pk;
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (f0 + e < p.M) dst[e] = __float2bfloat16_rn(v[e]);
+                }
+              } else {
+                float* dst = reinterpret_cast<float*>(p.out[0]) + off;
+                if (full4 && (p.ldo[0] & 3) == 0) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else if (full4 && (p.ldo[0] & 1) == 0) {
+                  *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+                  *reinterpret_cast<float2*>(dst + 2) = make_float2(v[2], v[3]);
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (f0 + e < p.M) dst[e] = v[e];
                 }
               }
             }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -327,6 +399,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (p.pdl) tl_mark(200000 + 1000 + static_cast<int>(gridDim.x));
+  if (chained && threadIdx.x == 0) chain_signal_thread0(p.chain);
   if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();
   if (warp == 2) {
     tc_fence_after();

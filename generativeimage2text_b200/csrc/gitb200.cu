@@ -77,7 +77,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TmapKey {
   const void* ptr;
   long long rows, cols, ld;
-  int box_rows;
+  int box_rows;   // negative: un-swizzled box (decode attention K/V slices)
   bool operator<(const TmapKey& o) const {
     if (ptr != o.ptr) return ptr < o.ptr;
     if (rows != o.rows) return rows < o.rows;
@@ -95,6 +95,7 @@ struct gitb200_engine {
   int64_t launches = 0;
   bool use_graph = true;
   bool use_pdl = true;
+  bool use_chain = true;
 
   // derived geometry
   int g = 0, L = 0, Kpatch = 0, Kp = 0, d = 0, D = 0, F = 0, V = 0;
@@ -115,6 +116,11 @@ struct gitb200_engine {
   DevBuf state, next_token, logprob_sum, tokens_i64, stage_img, stage_tok, stage_lp, prefix_dev;
   DevBuf beam_ws;                                           // beam-search bookkeeping (search.cuh)
   DevBuf sel_ws;                                            // greedy selection partials
+  DevBuf chain;                                             // decode-step kernel chain completion counters [64]
+  unsigned int last_chain_ctas = 0;                         // CTAs of the last kernel launched by step_layers
+  int last_chain_idx = 0;
+  int attn_chunk_rows = 0, attn_box_rows = 0;
+  size_t attn_smem = 0;
   int cur_B = 0, cur_frames = 0, cur_M = 0, cur_beam = 1, T_alloc = 0, cur_rows = 0, cur_src = 0;
 
   EncodeTiledFn encode_tiled = nullptr;
@@ -124,6 +130,7 @@ struct gitb200_engine {
   cudaGraphExec_t step_graph = nullptr;
   std::vector<long long> step_graph_key;
   int64_t launches_per_step = 0;
+  int last_gemm_grid = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t own_event = nullptr;
 };
@@ -187,10 +194,11 @@ static int load_encode_fn(gitb200_engine* h) {
   return 0;
 }
 
-// bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows x 64] swizzle-128B.
+// bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows x 64], 128B-swizzled (GEMM
+// operands) or plain row-major (swizzle == false: decode-attention K/V slices).
 static int get_tmap(gitb200_engine* h, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
-                    CUtensorMap* out) {
-  TmapKey key{ptr, rows, cols, ld, box_rows};
+                    CUtensorMap* out, bool swizzle = true) {
+  TmapKey key{ptr, rows, cols, ld, swizzle ? box_rows : -box_rows};
   auto it = h->tmaps.find(key);
   if (it != h->tmaps.end()) {
     *out = it->second;
@@ -205,7 +213,7 @@ static int get_tmap(gitb200_engine* h, const void* ptr, long long rows, long lon
   cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = h->encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%d)",
                                      static_cast<int>(r), rows, cols, ld, box_rows);
@@ -242,6 +250,7 @@ static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st)
   const int n_tiles = (c.p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles * c.p.k_splits;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  h->last_gemm_grid = grid;
   CK(launch_k(c.p.pdl != 0, gemm_bf16_tcgen05<BN>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
   CKL(h, "gemm_bf16_tcgen05");
   return 0;
@@ -377,9 +386,10 @@ __global__ void cvt_rows_kernel(const float* __restrict__ src, long long src_ld,
     dst[r * dst_ld + c] = __float2bfloat16_rn(c < cols ? src[r * src_ld + c] : 0.0f);
   }
 }
-__global__ void set_state_kernel(StepState* st, int pos, int cur_len) {
+__global__ void set_state_kernel(StepState* st, int pos, int cur_len, unsigned int* chain) {
   st->pos = pos; st->cur_len = cur_len; st->finished = 0; st->final_len = cur_len; st->step = 0;
   st->empty_caption = 0; st->ticket = 0; st->not_eos = 0;
+  for (int k = 0; k < 64; ++k) chain[k] = 0;
 }
 __global__ void init_generate_kernel(long long* tokens_out, long long* next_token, float* logprob_sum,
                                      const long long* prefix, int P, int rows, int max_steps, int sos) {
@@ -389,10 +399,12 @@ __global__ void init_generate_kernel(long long* tokens_out, long long* next_toke
   next_token[r] = prefix ? prefix[0] : sos;
   logprob_sum[r] = 0.f;
 }
-__global__ void advance_prefix_kernel(StepState* st, long long* next_token, const long long* prefix, int idx, int rows) {
+__global__ void advance_prefix_kernel(StepState* st, long long* next_token, const long long* prefix, int idx, int rows,
+                                      unsigned int* chain) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) next_token[r] = prefix[idx];
   if (r == 0) st->pos = st->pos + 1;
+  if (r < 64) chain[r] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,6 +420,7 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (!h || !name) return 1;
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
+  if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
   return fail(h, "unknown option %s", name);
 }
 
@@ -453,7 +466,7 @@ static void release_all(gitb200_engine* h) {
                     &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->txt_kv, &h->src_row[0],
                     &h->src_row[1], &h->xd_t, &h->hd_t, &h->qkv_t, &h->ctx_t, &h->t_t, &h->u_t, &h->logits, &h->state,
                     &h->next_token, &h->logprob_sum, &h->tokens_i64, &h->stage_img, &h->stage_tok, &h->stage_lp,
-                    &h->prefix_dev, &h->beam_ws, &h->sel_ws};
+                    &h->prefix_dev, &h->beam_ws, &h->sel_ws, &h->chain};
   for (DevBuf* b : bufs) b->release();
   for (auto& l : h->enc) {
     DevBuf* lb[] = {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.ln2g, &l.ln2b, &l.w1, &l.b1, &l.w2, &l.b2};
@@ -803,47 +816,82 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
   float* t = h->t_t.as<float>();
   bf16* u = h->u_t.as<bf16>();
   const bool pdl = h->use_pdl;
-  CK(launch_k(pdl, embed_ln_kernel<768>, dim3((R + 7) / 8), dim3(256), 0, st, tokens, 1LL, h->words_f32.as<float>(),
+  // Ordering inside the step: flag chain (greedy; the beam bookkeeping kernels still use grid dependencies).
+  const bool chain_on = pdl && h->use_chain && beam == 1;
+  ChainSync cs{};
+  cs.counters = chain_on ? h->chain.as<unsigned int>() : nullptr;
+  cs.idx = 0;
+  cs.pred_ctas = 0;
+  auto next_link = [&](unsigned int ctas_of_this_kernel) {  // call after each launch
+    cs.idx += 1;
+    cs.pred_ctas = ctas_of_this_kernel;
+  };
+  // chain head: launched WITHOUT the PDL attribute -> fully ordered after the previous step
+  CK(launch_k(false, embed_ln_kernel<768>, dim3((R + 7) / 8), dim3(256), 0, st, tokens, 1LL, h->words_f32.as<float>(),
               h->positions.as<float>(), h->lnemb_g.as<float>(), h->lnemb_b.as<float>(), xd, hd, R, 0,
-              static_cast<const StepState*>(state), h->V));
+              static_cast<const StepState*>(state), h->V, cs));
   CKL(h, "embed_ln_kernel");
+  next_link((R + 7) / 8);
   // Split-K factors: a handful of activation rows against [features, K] weights is latency bound, so the K
   // dimension is spread over enough CTAs that each one has all of its weight tiles in flight at once
   // (partials meet in fp32 atomics; bias / residual / LayerNorm live in the consumer kernel).
+  auto skinny = [&](GemmCall c) -> int {
+    c.p.chain = cs;
+    TRY(launch_gemm(h, c, st));
+    next_link(static_cast<unsigned int>(h->last_gemm_grid));
+    return 0;
+  };
+  auto ln = [&](LnParams p) -> int {
+    p.zero_x = 1; p.skip_flag = skip; p.chain = cs;
+    TRY(launch_ln(h, p, D, st, pdl));
+    next_link((p.rows + 7) / 8);
+    return 0;
+  };
   for (int j = 0; j < nl; ++j) {
     DecLayer& l = h->dec[j];
-    TRY(launch_gemm(h, gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, nullptr, ACT_NONE, qkv, 3 * D, false, 3, skip, pdl), st));
+    TRY(skinny(gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, nullptr, ACT_NONE, qkv, 3 * D, false, 3, skip, pdl)));
     DecAttnParams ap{};
     ap.qkv = qkv; ap.bqkv = l.bqkv.as<float>(); ap.img_k = img_kv_ptr(h, j, 0); ap.img_v = img_kv_ptr(h, j, 1);
     ap.txt_k = txt_kv_ptr(h, j, 0); ap.txt_v = txt_kv_ptr(h, j, 1);
     ap.src_row = src_row; ap.ctx = ctx; ap.B = h->cur_B; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
     ap.state = state;
+    ap.chunk_rows = h->attn_chunk_rows; ap.box_rows = h->attn_box_rows;
+    ap.chain = cs;
+    CUtensorMap tk, tv;
+    TRY(get_tmap(h, ap.img_k, static_cast<long long>(h->cur_B) * h->cur_M, D, D, ap.box_rows, &tk, false));
+    TRY(get_tmap(h, ap.img_v, static_cast<long long>(h->cur_B) * h->cur_M, D, D, ap.box_rows, &tv, false));
     dim3 grid(h->cfg.dec_heads, h->cur_B);
-    if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), 0, st, ap));
-    else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), 0, st, ap));
+    if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+    else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
     CKL(h, "decode_attn_kernel");
-    TRY(launch_gemm(h, gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 6, skip, pdl), st));
-    {
-      LnParams p = ln_params(t, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, R);
-      p.zero_x = 1; p.skip_flag = skip;
-      TRY(launch_ln(h, p, D, st, pdl));
-    }
-    TRY(launch_gemm(h, gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip, pdl), st));
-    TRY(launch_gemm(h, gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, 12, skip, pdl), st));
-    {
-      LnParams p = ln_params(t, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, R);
-      p.zero_x = 1; p.skip_flag = skip;
-      TRY(launch_ln(h, p, D, st, pdl));
-    }
+    next_link(grid.x * grid.y);
+    TRY(skinny(gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 6, skip, pdl)));
+    TRY(ln(ln_params(t, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, R)));
+    TRY(skinny(gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip, pdl)));
+    TRY(skinny(gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, 12, skip, pdl)));
+    TRY(ln(ln_params(t, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, R)));
   }
   if (lm_head)
-    TRY(launch_gemm(h, gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, h->logits.p, h->V, false, 1, skip, pdl), st));
+    TRY(skinny(gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, h->logits.p, h->V, false, 1, skip, pdl)));
+  h->last_chain_idx = cs.idx;
+  h->last_chain_ctas = cs.pred_ctas;
   return 0;
 }
 
+// Geometry of the decode-attention staging buffer: the image K/V slice of one (image, head) is M rows of 128 B;
+// up to 512 rows are staged per round as 1-2 TMA boxes of <= 256 rows.
 static int set_attn_smem_limit(gitb200_engine* h) {
-  (void)h;  // the single-pass decode attention keeps no per-key scores in shared memory
+  const int M = h->cur_M;
+  const int chunk = M < 512 ? M : 512;
+  const int nb = (chunk + 255) / 256;
+  h->attn_box_rows = (chunk + nb - 1) / nb;
+  h->attn_chunk_rows = h->attn_box_rows * nb;
+  h->attn_smem = static_cast<size_t>(2) * h->attn_chunk_rows * 128 + 128;
+  CK(cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
+  CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
+  CK(h->chain.ensure(256));
+  CK(cudaMemset(h->chain.p, 0, 256));
   return 0;
 }
 

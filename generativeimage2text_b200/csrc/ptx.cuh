@@ -35,11 +35,61 @@ __device__ __forceinline__ void tl_mark(int kid) {
   }
 }
 
+// same, for one designated thread of block 0 that is not thread 0
+__device__ __forceinline__ void tl_mark_one(int kid) {
+  if (g_tl_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    const unsigned int i = atomicAdd(&g_tl_count, 1u);
+    if (i < kTimelineMax) {
+      g_tl_buf[2 * i] = globaltimer_ns();
+      g_tl_buf[2 * i + 1] = static_cast<unsigned long long>(kid);
+    }
+  }
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
 // start while its predecessor is still running; griddep_wait() blocks until the predecessor grid has completed
 // and its writes are visible, griddep_launch() lets the successor's prologue begin. Both are no-ops otherwise.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Flag-based ordering of the decode-step kernel chain.  Kernel k of a step (launched with the PDL attribute, so
+// it may become resident while kernel k-1 still runs, but WITHOUT griddepcontrol.wait) spins until every CTA of
+// kernel k-1 has published its completion; kernel boundaries then cost one L2 round trip instead of a full grid
+// drain + memory flush (~4 us measured).  Safe against deadlock because a PDL successor is only scheduled once
+// every CTA of its predecessor has started.  Data written under this scheme must be read with L1-bypassing
+// loads (__ldcg / TMA).  Counters are re-zeroed by the last kernel of the step.
+struct ChainSync {
+  unsigned int* counters;   // [64] (null: disabled)
+  int idx;                  // position of this kernel in the step's chain
+  unsigned int pred_ctas;   // CTAs of kernel idx-1
+};
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all threads of the CTA
+__device__ __forceinline__ void chain_wait(const ChainSync& c) {
+  if (c.counters != nullptr && c.idx > 0) {
+    if (threadIdx.x == 0) {
+      while (ld_acquire_gpu(c.counters + c.idx - 1) < c.pred_ctas) {
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");  // thread 0 is also the TMA issuer of every kernel here
+    }
+    __syncthreads();
+  }
+}
+// thread 0, after a __syncthreads() that follows the CTA's last global write
+__device__ __forceinline__ void chain_signal_thread0(const ChainSync& c) {
+  __threadfence();
+  atomicAdd(c.counters + c.idx, 1u);
+}
+__device__ __forceinline__ void chain_signal(const ChainSync& c) {
+  if (c.counters != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) chain_signal_thread0(c);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier

@@ -35,6 +35,7 @@ struct LnParams {
   const float* temb;     // [F, D] or null
   int remap_B, remap_F, remap_L;  // remap_F == 0 -> identity
   const int* skip_flag;  // device int: non-zero -> kernel is a no-op (finished decode)
+  ChainSync chain;       // decode-step flag ordering (counters == null: plain / PDL ordering)
 };
 
 template <int D>
@@ -42,36 +43,50 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   static_assert(D % 128 == 0, "D");
   constexpr int NV = D / 128;
   griddep_launch();
-  griddep_wait();
-  tl_mark(2);
-  if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  tl_mark(100002);
   const int lane = threadIdx.x & 31;
+  // parameters are constants: fetch them before the dependency wait
+  float4 gam[NV], bet[NV], bia[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    gam[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + i * 32 + lane);
+    bet[i] = __ldg(reinterpret_cast<const float4*>(p.beta) + i * 32 + lane);
+    bia[i] = (p.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.bias) + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const bool chained = p.chain.counters != nullptr;
+  if (chained) {
+    if (p.skip_flag != nullptr && *p.skip_flag != 0) return;  // stable within a step
+    chain_wait(p.chain);
+  } else {
+    griddep_wait();
+    if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
+  }
+  tl_mark(2);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) {
+    chain_signal(p.chain);
+    return;
+  }
   float4 v[NV];
   const float4* xp = reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * D);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = xp[i * 32 + lane];
+  for (int i = 0; i < NV; ++i) v[i] = __ldcg(xp + i * 32 + lane);
+  if (p.resid != nullptr) {
+    const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 r = __ldcg(rp + i * 32 + lane);
+      v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+    }
+  }
   if (p.zero_x) {
     float4* zp = reinterpret_cast<float4*>(const_cast<float*>(p.x) + static_cast<long long>(row) * D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) zp[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (p.bias != nullptr) {
-    const float4* bp = reinterpret_cast<const float4*>(p.bias);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 b = __ldg(bp + i * 32 + lane);
-      v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
-    }
-  }
-  if (p.resid != nullptr) {
-    const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * D);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 r = rp[i * 32 + lane];
-      v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
-    }
+  for (int i = 0; i < NV; ++i) {
+    v[i].x += bia[i].x; v[i].y += bia[i].y; v[i].z += bia[i].z; v[i].w += bia[i].w;
   }
   float s = 0.f;
 #pragma unroll
@@ -94,12 +109,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     const int b = img - frame * p.remap_B;
     orow = (static_cast<long long>(b) * p.remap_F + frame) * p.remap_L + l;
   }
-  const float4* gp = reinterpret_cast<const float4*>(p.gamma);
-  const float4* bp = reinterpret_cast<const float4*>(p.beta);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const float4 g = __ldg(gp + i * 32 + lane);
-    const float4 b = __ldg(bp + i * 32 + lane);
+    const float4 g = gam[i];
+    const float4 b = bet[i];
     float4 o;
     o.x = (v[i].x - mean) * rstd * g.x + b.x;
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -117,6 +130,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       reinterpret_cast<uint2*>(p.out_bf16 + orow * D)[i * 32 + lane] = pk;
     }
   }
+  tl_mark(200002);
+  chain_signal(p.chain);
 }
 
 // Patch im2col for the stride==kernel conv (reference layers/CLIP/model.py:224,242):
@@ -203,14 +218,17 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const long long* __restrict__ tokens, long long tok_stride, const float* __restrict__ words,
                 const float* __restrict__ positions, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int rows, int pos_base,
-                const StepState* __restrict__ state, int vocab) {
+                const StepState* __restrict__ state, int vocab, const ChainSync chain) {
   constexpr int NV = D / 128;
   griddep_launch();
-  griddep_wait();
+  griddep_wait();   // chain head: ordered after the previous step by a full dependency
   tl_mark(4);
   if (state != nullptr && state->finished) return;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  if (row >= rows) {
+    chain_signal(chain);
+    return;
+  }
   const int lane = threadIdx.x & 31;
   long long tok = tokens[row * tok_stride];
   tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
@@ -246,6 +264,7 @@ embed_ln_kernel(const long long* __restrict__ tokens, long long tok_stride, cons
     pk.y = pack_bf16(o.z, o.w);
     reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[i * 32 + lane] = pk;
   }
+  chain_signal(chain);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -273,16 +292,23 @@ struct SelectParams {
   float* part_sum;          // [rows, n_split]  sum exp(v - part_max)
   int* part_arg;            // [rows, n_split]
   unsigned int* row_ticket; // [rows]
+  ChainSync chain;          // last kernel of the chain: waits, then re-zeroes all counters when the step is over
 };
 
 // grid (n_split, rows): each CTA folds one vocabulary slice of one row into (max, argmax, sum exp) with a
 // single online pass; the last CTA of a row combines the slices and does the reference's bookkeeping.
 __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p) {
   griddep_launch();
-  griddep_wait();
-  tl_mark(5);
+  tl_mark(100005);
   StepState* st = p.state;
-  if (st->finished) return;
+  if (p.chain.counters != nullptr) {
+    if (st->finished) return;  // stable within a step
+    chain_wait(p.chain);
+  } else {
+    griddep_wait();
+    if (st->finished) return;
+  }
+  tl_mark(5);
   const int row = blockIdx.y;
   const int split = blockIdx.x;
   const int tid = threadIdx.x;
@@ -302,16 +328,16 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
   }
   float m = -INFINITY, ssum = 0.f;
   int arg = 0x7fffffff;
-  for (int i0 = lo + tid; i0 < hi; i0 += 4 * 256) {
-    float v[4];
+  for (int i0 = lo + tid; i0 < hi; i0 += 16 * 256) {   // one round for the usual 8-way split of 30522
+    float v[16];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const int i = i0 + u * 256;
-      v[u] = (i < hi) ? z[i] : -INFINITY;
+      v[u] = (i < hi) ? __ldcg(z + i) : -INFINITY;
       if (!first && i == static_cast<int>(last)) v[u] = -10000.0f;   // no-repeat (reference :330)
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const int i = i0 + u * 256;
       if (v[u] > m) {   // increasing i per thread: keeps the lowest index on exact ties
         ssum = ssum * __expf(m - v[u]) + 1.0f;
@@ -403,6 +429,9 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
           if (first) st->empty_caption = 1;
         }
         if (cur_len + 1 >= p.max_steps) st->finished = 1;
+        // every CTA of every kernel of this step has passed its wait: recycle the chain counters
+        if (p.chain.counters != nullptr)
+          for (int k = 0; k < 64; ++k) p.chain.counters[k] = 0;
         __threadfence();
       }
     }
