@@ -225,213 +225,254 @@ __device__ __forceinline__ void dec_attn_update(float (&sc)[4], const uint4 (&w)
   m = m_new;
 }
 
-// grid (heads, images); 128 threads = 16 key groups x 8 lanes (8 head dims each, 128-bit accesses).
-// The image K/V slice of this (image, head) -- M rows of 128 bytes, constant during decoding -- is fetched by
-// TMA into shared memory BEFORE the dependency wait, so under programmatic dependent launch the HBM stream of
-// this kernel overlaps the QKV GEMM that precedes it; after the wait only the new token's q/k/v, the short
-// text history and the arithmetic remain.  Scores are folded into per-group online-softmax states that are
-// merged at the end (flash-decoding style), single pass over K and V.
+// Persistent, double-buffered streaming kernel: CTA c handles the (image, head) items c, c+G, c+2G, ...  Each item's
+// image K/V slice (M rows of 128 B, constant during decoding) is fetched by TMA into one of two shared-memory
+// buffers; the first two fetches are issued BEFORE the dependency wait, so under programmatic dependent launch most
+// of this kernel's HBM stream overlaps the QKV GEMM that precedes it, and later fetches overlap the arithmetic of
+// the previous item.  128 threads = 16 key groups x 8 lanes (8 head dims each, 128-bit accesses); scores are folded
+// into per-group online-softmax states merged at the end (flash-decoding style), single pass over K and V.
 template <int NQ>
 __global__ void __launch_bounds__(128)
 decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const DecAttnParams p) {
   extern __shared__ uint8_t attn_dyn[];
-  uint8_t* sK = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_dyn) + 127) & ~uintptr_t(127));
-  uint8_t* sV = sK + static_cast<size_t>(p.chunk_rows) * 128;
-  __shared__ uint64_t bar;
+  uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_dyn) + 127) & ~uintptr_t(127));
+  const size_t kv_bytes = static_cast<size_t>(p.chunk_rows) * 128;  // one of K / V of one unit
+  __shared__ uint64_t bars[2];
   __shared__ float q_s[NQ][64];
   __shared__ float red_m[4][NQ];
   __shared__ float red_l[4][NQ];
   __shared__ float red_acc[4][NQ][64];
 
-  const int h = blockIdx.x;
-  const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int D = p.D;
+  const int H = D / 64;
+  const int n_items = p.B * H;
+  const int G = gridDim.x;
   const int n_chunks = (p.M + p.chunk_rows - 1) / p.chunk_rows;
+  const int n_my = (n_items - static_cast<int>(blockIdx.x) + G - 1) / G;
+  const int n_units = n_my * n_chunks;
 
   griddep_launch();
   tl_mark(100003);
   if (tid == 0) {
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(&bar, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  auto issue_chunk = [&](int c) {  // one thread
+  auto issue_unit = [&](int u) {  // one thread
+    const int item = blockIdx.x + (u / n_chunks) * G;
+    const int c = u - (u / n_chunks) * n_chunks;
+    const int b = item / H, h = item - b * H;
+    uint8_t* sK = sbase + static_cast<size_t>(u & 1) * 2 * kv_bytes;
+    uint8_t* sV = sK + kv_bytes;
     const int rows_c = min(p.chunk_rows, p.M - c * p.chunk_rows);
     const int nb = (rows_c + p.box_rows - 1) / p.box_rows;
-    mbar_arrive_expect_tx(&bar, static_cast<uint32_t>(2 * nb * p.box_rows * 128));
+    mbar_arrive_expect_tx(&bars[u & 1], static_cast<uint32_t>(2 * nb * p.box_rows * 128));
     for (int i = 0; i < nb; ++i) {
       const int grow = b * p.M + c * p.chunk_rows + i * p.box_rows;
-      tma_load_2d(sK + static_cast<size_t>(i) * p.box_rows * 128, &tmK, &bar, h * 64, grow);
-      tma_load_2d(sV + static_cast<size_t>(i) * p.box_rows * 128, &tmV, &bar, h * 64, grow);
+      tma_load_2d(sK + static_cast<size_t>(i) * p.box_rows * 128, &tmK, &bars[u & 1], h * 64, grow);
+      tma_load_2d(sV + static_cast<size_t>(i) * p.box_rows * 128, &tmV, &bars[u & 1], h * 64, grow);
     }
   };
-  if (tid == 0) issue_chunk(0);
+  if (tid == 0) {
+    issue_unit(0);
+    if (n_units > 1) issue_unit(1);
+  }
+  bool finished;
   if (p.chain.counters != nullptr) {
     // `finished` only changes between steps (full dependency): in a finished step no kernel waits or signals
-    if (p.state != nullptr && p.state->finished) {
-      mbar_wait(&bar, 0);  // never leave with a bulk copy in flight into this CTA's shared memory
-      return;
-    }
-    chain_wait(p.chain);
+    finished = (p.state != nullptr && p.state->finished);
+    if (!finished) chain_wait(p.chain);
   } else {
     griddep_wait();
-    if (p.state != nullptr && p.state->finished) {
-      mbar_wait(&bar, 0);
-      return;
-    }
+    finished = (p.state != nullptr && p.state->finished);
+  }
+  if (finished) {  // never leave with a bulk copy in flight into this CTA's shared memory
+    mbar_wait(&bars[0], 0);
+    if (n_units > 1) mbar_wait(&bars[1], 0);
+    return;
   }
   tl_mark(3);
   const int pos = (p.state != nullptr) ? p.state->pos : p.pos_fixed;
   const int n_txt = pos + 1;
-
-  // ---- q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V (bf16) ----
-  for (int qi = 0; qi < NQ; ++qi) {
-    const int r = b * NQ + qi;
-    float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
-    const float* bias = p.bqkv + h * 64;
-    if (tid < 64) {
-      q_s[qi][tid] = (__ldcg(row + tid) + bias[tid]) * 0.125f;
-      p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(__ldcg(row + D + tid) + bias[D + tid]);
-      row[tid] = 0.f;
-      row[D + tid] = 0.f;
-    } else {
-      const int d = tid - 64;
-      p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(__ldcg(row + 2 * D + d) + bias[2 * D + d]);
-      row[2 * D + d] = 0.f;
-    }
-  }
-  __syncthreads();
-
   const int grp = tid >> 3;
   const int gl = tid & 7;
-  float qreg[NQ][8];
-  float m_run[NQ], l_run[NQ], acc[NQ][8];
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  // This step's q/k/v of every item of this CTA are requested together (one L2 round trip instead of one per item):
+  // threads 0-63 hold (q, k) of dim tid, threads 64-127 hold v of dim tid-64.
+  constexpr int kPre = (NQ == 1) ? 4 : 1;
+  float pre_a[kPre], pre_b[kPre];
 #pragma unroll
-  for (int qi = 0; qi < NQ; ++qi) {
-    m_run[qi] = -INFINITY;
-    l_run[qi] = 0.f;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      qreg[qi][d] = q_s[qi][gl * 8 + d];
-      acc[qi][d] = 0.f;
+  for (int k = 0; k < kPre; ++k) {
+    pre_a[k] = 0.f;
+    pre_b[k] = 0.f;
+    if (NQ == 1 && k < n_my) {
+      const int item = blockIdx.x + k * G;
+      const int b = item / H, h = item - b * H;
+      const float* row = p.qkv + static_cast<long long>(b) * 3 * D + h * 64;
+      if (tid < 64) {
+        pre_a[k] = __ldcg(row + tid);
+        pre_b[k] = __ldcg(row + D + tid);
+      } else {
+        pre_a[k] = __ldcg(row + 2 * D + tid - 64);
+      }
     }
   }
 
-  // ---- text keys first (global loads; the TMA of the image slice is still landing) ----
-  // each beam row has its own history (through the src_row indirection)
+  for (int k = 0; k < n_my; ++k) {
+    const int item = blockIdx.x + k * G;
+    const int b = item / H, h = item - b * H;
+    // ---- q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V (bf16) ----
+    for (int qi = 0; qi < NQ; ++qi) {
+      const int r = b * NQ + qi;
+      float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
+      const float* bias = p.bqkv + h * 64;
+      const bool have = (NQ == 1) && (k < kPre);
+      if (tid < 64) {
+        const float qv = have ? pre_a[k < kPre ? k : 0] : __ldcg(row + tid);
+        const float kv = have ? pre_b[k < kPre ? k : 0] : __ldcg(row + D + tid);
+        q_s[qi][tid] = (qv + bias[tid]) * 0.125f;
+        p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(kv + bias[D + tid]);
+        row[tid] = 0.f;
+        row[D + tid] = 0.f;
+      } else {
+        const int d = tid - 64;
+        const float vv = have ? pre_a[k < kPre ? k : 0] : __ldcg(row + 2 * D + d);
+        p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(vv + bias[2 * D + d]);
+        row[2 * D + d] = 0.f;
+      }
+    }
+    __syncthreads();
+
+    float qreg[NQ][8];
+    float m_run[NQ], l_run[NQ], acc[NQ][8];
 #pragma unroll
-  for (int qi = 0; qi < NQ; ++qi) {
-    const int r = b * NQ + qi;
-    for (int base = 0; base < n_txt; base += 64) {
-      uint4 u[4], w[4];
+    for (int qi = 0; qi < NQ; ++qi) {
+      m_run[qi] = -INFINITY;
+      l_run[qi] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = base + grp + 16 * i;
-        if (j < n_txt) {
-          const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
-          const long long off = (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8;
-          u[i] = *reinterpret_cast<const uint4*>(p.txt_k + off);
-          w[i] = *reinterpret_cast<const uint4*>(p.txt_v + off);
-        } else {
-          u[i] = make_uint4(0, 0, 0, 0);
-          w[i] = make_uint4(0, 0, 0, 0);
+      for (int d = 0; d < 8; ++d) {
+        qreg[qi][d] = q_s[qi][gl * 8 + d];
+        acc[qi][d] = 0.f;
+      }
+    }
+    // ---- text keys (global loads): each beam row has its own history (through the src_row indirection) ----
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+      const int r = b * NQ + qi;
+      for (int base = 0; base < n_txt; base += 64) {
+        uint4 u[4], w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = base + grp + 16 * i;
+          if (j < n_txt) {
+            const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
+            const long long off = (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8;
+            u[i] = *reinterpret_cast<const uint4*>(p.txt_k + off);
+            w[i] = *reinterpret_cast<const uint4*>(p.txt_v + off);
+          } else {
+            u[i] = make_uint4(0, 0, 0, 0);
+            w[i] = make_uint4(0, 0, 0, 0);
+          }
         }
-      }
-      float sc[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float kf[8];
-        bf16x8_to_f32(u[i], kf);
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[d], a);
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        sc[i] = (base + grp + 16 * i < n_txt) ? a : -INFINITY;
-      }
-      dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
-    }
-  }
-  // ---- image keys from shared memory: shared by the NQ beams of this image ----
-  for (int c = 0; c < n_chunks; ++c) {
-    if (c > 0) {
-      __syncthreads();  // everyone is done with the previous chunk
-      if (tid == 0) issue_chunk(c);
-    }
-    mbar_wait(&bar, static_cast<uint32_t>(c & 1));
-    const int rows_c = min(p.chunk_rows, p.M - c * p.chunk_rows);
-    for (int base = 0; base < rows_c; base += 64) {  // uniform trip count: the shuffles below stay converged
-      uint4 u[4], w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int s = base + grp + 16 * i;
-        const bool ok = s < rows_c;
-        u[i] = ok ? *reinterpret_cast<const uint4*>(sK + static_cast<size_t>(s) * 128 + gl * 16) : make_uint4(0, 0, 0, 0);
-        w[i] = ok ? *reinterpret_cast<const uint4*>(sV + static_cast<size_t>(s) * 128 + gl * 16) : make_uint4(0, 0, 0, 0);
-      }
-      float kf[4][8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) bf16x8_to_f32(u[i], kf[i]);
-#pragma unroll
-      for (int qi = 0; qi < NQ; ++qi) {
         float sc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          float kf[8];
+          bf16x8_to_f32(u[i], kf);
           float a = 0.f;
 #pragma unroll
-          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[i][d], a);
+          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[d], a);
           a += __shfl_xor_sync(0xffffffffu, a, 1);
           a += __shfl_xor_sync(0xffffffffu, a, 2);
           a += __shfl_xor_sync(0xffffffffu, a, 4);
-          sc[i] = (base + grp + 16 * i < rows_c) ? a : -INFINITY;
+          sc[i] = (base + grp + 16 * i < n_txt) ? a : -INFINITY;
         }
         dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
       }
     }
-  }
-  // ---- merge the 16 group states: 4 groups of a warp by shuffles, the 4 warps through smem ----
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
+    // ---- image keys from shared memory: shared by the NQ beams of this image ----
+    for (int c = 0; c < n_chunks; ++c) {
+      const int u_idx = k * n_chunks + c;
+      const uint8_t* sK = sbase + static_cast<size_t>(u_idx & 1) * 2 * kv_bytes;
+      const uint8_t* sV = sK + kv_bytes;
+      mbar_wait(&bars[u_idx & 1], static_cast<uint32_t>((u_idx >> 1) & 1));
+      const int rows_c = min(p.chunk_rows, p.M - c * p.chunk_rows);
+      for (int base = 0; base < rows_c; base += 64) {  // uniform trip count: the shuffles below stay converged
+        uint4 u[4], w[4];
 #pragma unroll
-  for (int qi = 0; qi < NQ; ++qi) {
+        for (int i = 0; i < 4; ++i) {
+          const int s = base + grp + 16 * i;
+          const bool ok = s < rows_c;
+          u[i] = ok ? *reinterpret_cast<const uint4*>(sK + static_cast<size_t>(s) * 128 + gl * 16) : make_uint4(0, 0, 0, 0);
+          w[i] = ok ? *reinterpret_cast<const uint4*>(sV + static_cast<size_t>(s) * 128 + gl * 16) : make_uint4(0, 0, 0, 0);
+        }
+        float kf[4][8];
 #pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      const float m_o = __shfl_xor_sync(0xffffffffu, m_run[qi], o);
-      const float l_o = __shfl_xor_sync(0xffffffffu, l_run[qi], o);
-      const float m_n = fmaxf(m_run[qi], m_o);
-      const float sa = (m_run[qi] == -INFINITY) ? 0.f : __expf(m_run[qi] - m_n);
-      const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - m_n);
-      l_run[qi] = l_run[qi] * sa + l_o * sb;
+        for (int i = 0; i < 4; ++i) bf16x8_to_f32(u[i], kf[i]);
 #pragma unroll
-      for (int d = 0; d < 8; ++d) {
-        const float a_o = __shfl_xor_sync(0xffffffffu, acc[qi][d], o);
-        acc[qi][d] = acc[qi][d] * sa + a_o * sb;
+        for (int qi = 0; qi < NQ; ++qi) {
+          float sc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[i][d], a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            sc[i] = (base + grp + 16 * i < rows_c) ? a : -INFINITY;
+          }
+          dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
+        }
       }
-      m_run[qi] = m_n;
+      __syncthreads();  // everyone is done with this buffer: refill it with the unit after next
+      if (tid == 0 && u_idx + 2 < n_units) issue_unit(u_idx + 2);
     }
-    if (lane < 8) {
-      if (lane == 0) { red_m[warp][qi] = m_run[qi]; red_l[warp][qi] = l_run[qi]; }
+    // ---- merge the 16 group states: 4 groups of a warp by shuffles, the 4 warps through smem ----
 #pragma unroll
-      for (int d = 0; d < 8; ++d) red_acc[warp][qi][lane * 8 + d] = acc[qi][d];
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < NQ * 64; i += 128) {
-    const int qi = i >> 6;
-    const int d = i & 63;
-    const float mm = fmaxf(fmaxf(red_m[0][qi], red_m[1][qi]), fmaxf(red_m[2][qi], red_m[3][qi]));
-    float l = 0.f, a = 0.f;
+    for (int qi = 0; qi < NQ; ++qi) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float sw = (red_m[w][qi] == -INFINITY) ? 0.f : __expf(red_m[w][qi] - mm);
-      l += red_l[w][qi] * sw;
-      a += red_acc[w][qi][d] * sw;
+      for (int o = 8; o <= 16; o <<= 1) {
+        const float m_o = __shfl_xor_sync(0xffffffffu, m_run[qi], o);
+        const float l_o = __shfl_xor_sync(0xffffffffu, l_run[qi], o);
+        const float m_n = fmaxf(m_run[qi], m_o);
+        const float sa = (m_run[qi] == -INFINITY) ? 0.f : __expf(m_run[qi] - m_n);
+        const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - m_n);
+        l_run[qi] = l_run[qi] * sa + l_o * sb;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          const float a_o = __shfl_xor_sync(0xffffffffu, acc[qi][d], o);
+          acc[qi][d] = acc[qi][d] * sa + a_o * sb;
+        }
+        m_run[qi] = m_n;
+      }
+      if (lane < 8) {
+        if (lane == 0) { red_m[warp][qi] = m_run[qi]; red_l[warp][qi] = l_run[qi]; }
+#pragma unroll
+        for (int d = 0; d < 8; ++d) red_acc[warp][qi][lane * 8 + d] = acc[qi][d];
+      }
     }
-    p.ctx[static_cast<long long>(b * NQ + qi) * D + h * 64 + d] = __float2bfloat16_rn(a / l);
+    __syncthreads();
+    for (int i = tid; i < NQ * 64; i += 128) {
+      const int qi = i >> 6;
+      const int d = i & 63;
+      const float mm = fmaxf(fmaxf(red_m[0][qi], red_m[1][qi]), fmaxf(red_m[2][qi], red_m[3][qi]));
+      float l = 0.f, a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float sw = (red_m[w][qi] == -INFINITY) ? 0.f : __expf(red_m[w][qi] - mm);
+        l += red_l[w][qi] * sw;
+        a += red_acc[w][qi][d] * sw;
+      }
+      p.ctx[static_cast<long long>(b * NQ + qi) * D + h * 64 + d] = __float2bfloat16_rn(a / l);
+    }
+    __syncthreads();  // q_s / red_* are reused by the next item
   }
   tl_mark(200003);
   chain_signal(p.chain);

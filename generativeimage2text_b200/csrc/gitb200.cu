@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -119,7 +120,7 @@ struct gitb200_engine {
   DevBuf chain;                                             // decode-step kernel chain completion counters [64]
   unsigned int last_chain_ctas = 0;                         // CTAs of the last kernel launched by step_layers
   int last_chain_idx = 0;
-  int attn_chunk_rows = 0, attn_box_rows = 0;
+  int attn_chunk_rows = 0, attn_box_rows = 0, attn_grid = 0;
   size_t attn_smem = 0;
   int cur_B = 0, cur_frames = 0, cur_M = 0, cur_beam = 1, T_alloc = 0, cur_rows = 0, cur_src = 0;
 
@@ -860,12 +861,12 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
     CUtensorMap tk, tv;
     TRY(get_tmap(h, ap.img_k, static_cast<long long>(h->cur_B) * h->cur_M, D, D, ap.box_rows, &tk, false));
     TRY(get_tmap(h, ap.img_v, static_cast<long long>(h->cur_B) * h->cur_M, D, D, ap.box_rows, &tv, false));
-    dim3 grid(h->cfg.dec_heads, h->cur_B);
+    dim3 grid(h->attn_grid);
     if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
     CKL(h, "decode_attn_kernel");
-    next_link(grid.x * grid.y);
+    next_link(grid.x);
     TRY(skinny(gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 6, skip, pdl)));
     TRY(ln(ln_params(t, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, R)));
     TRY(skinny(gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip, pdl)));
@@ -883,11 +884,15 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
 // up to 512 rows are staged per round as 1-2 TMA boxes of <= 256 rows.
 static int set_attn_smem_limit(gitb200_engine* h) {
   const int M = h->cur_M;
-  const int chunk = M < 512 ? M : 512;
+  const int chunk = M <= 384 ? M : 256;   // two (K + V) buffers of `chunk` rows must fit in shared memory
   const int nb = (chunk + 255) / 256;
   h->attn_box_rows = (chunk + nb - 1) / nb;
   h->attn_chunk_rows = h->attn_box_rows * nb;
-  h->attn_smem = static_cast<size_t>(2) * h->attn_chunk_rows * 128 + 128;
+  // two buffers (K + V each) per CTA; two CTAs per SM when they fit next to each other
+  h->attn_smem = static_cast<size_t>(4) * h->attn_chunk_rows * 128 + 128;
+  const int per_sm = (h->attn_smem * 2 + 8 * 1024 <= 227 * 1024) ? 2 : 1;
+  const int items = h->cur_B * h->cfg.dec_heads;
+  h->attn_grid = std::min(items, per_sm * h->num_sms);
   CK(cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(h->chain.ensure(256));

@@ -33,5 +33,5 @@ idx = [i for i, (t, k) in enumerate(ev) if k == 4]
 a, b = idx[12], idx[13]
 t0 = ev[a][0]
 for t, k in ev[a:b + 1]:
-    ph = {0: 'ready ', 1: 'START ', 2: 'end   '}[k // 100000]
+    ph = {0: 'ready ', 1: 'START ', 2: 'end   ', 3: ' data ', 4: ' epi  '}[k // 100000]
     print('%9.2f us  %s %s' % ((t - t0) * 1e-3, ph, nm(k)))
