@@ -118,8 +118,6 @@ struct gitb200_engine {
   DevBuf beam_ws;                                           // beam-search bookkeeping (search.cuh)
   DevBuf sel_ws;                                            // greedy selection partials
   DevBuf chain;                                             // decode-step kernel chain completion counters [64]
-  unsigned int last_chain_ctas = 0;                         // CTAs of the last kernel launched by step_layers
-  int last_chain_idx = 0;
   int attn_chunk_rows = 0, attn_box_rows = 0, attn_grid = 0;
   size_t attn_smem = 0;
   int cur_B = 0, cur_frames = 0, cur_M = 0, cur_beam = 1, T_alloc = 0, cur_rows = 0, cur_src = 0;
@@ -134,6 +132,22 @@ struct gitb200_engine {
   int last_gemm_grid = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t own_event = nullptr;
+  // decode lanes: the greedy batch is split into independent row groups whose (latency-bound) kernel chains run
+  // concurrently on separate streams -- forked and joined inside the captured step graph
+  int lanes_opt = 2;
+  cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+constexpr int kMaxLanes = 4;
+struct Lane {
+  int idx = 0;
+  int row0 = 0, rows = 0;   // sequences (images * beam)
+  int b0 = 0, nb = 0;       // images
+  cudaStream_t st = nullptr;
+  int chain_idx = 0;        // out: chain position / CTAs of the last kernel launched by step_layers
+  unsigned int chain_ctas = 0;
 };
 
 static int fail(gitb200_engine* h, const char* fmt, ...) {
@@ -387,7 +401,9 @@ __global__ void cvt_rows_kernel(const float* __restrict__ src, long long src_ld,
     dst[r * dst_ld + c] = __float2bfloat16_rn(c < cols ? src[r * src_ld + c] : 0.0f);
   }
 }
-__global__ void set_state_kernel(StepState* st, int pos, int cur_len, unsigned int* chain) {
+__global__ void set_state_kernel(StepState* states, int pos, int cur_len, unsigned int* chains) {
+  StepState* st = states + blockIdx.x;
+  unsigned int* chain = chains + blockIdx.x * 64;
   st->pos = pos; st->cur_len = cur_len; st->finished = 0; st->final_len = cur_len; st->step = 0;
   st->empty_caption = 0; st->ticket = 0; st->not_eos = 0;
   for (int k = 0; k < 64; ++k) chain[k] = 0;
@@ -422,6 +438,7 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
+  if (strcmp(name, "lanes") == 0) { h->lanes_opt = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : static_cast<int>(value)); return 0; }
   return fail(h, "unknown option %s", name);
 }
 
@@ -484,6 +501,8 @@ extern "C" void gitb200_destroy(gitb200_engine* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  for (int i = 0; i < kMaxLanes; ++i) { if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->own_event) cudaEventDestroy(h->own_event);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   release_all(h);
@@ -757,7 +776,7 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
   CK(h->t_t.ensure(static_cast<size_t>(R) * D * 4));
   CK(h->u_t.ensure(static_cast<size_t>(R) * F * 2));
   CK(h->logits.ensure(static_cast<size_t>(R) * h->V * 4));
-  CK(h->state.ensure(sizeof(StepState)));
+  CK(h->state.ensure(sizeof(StepState) * kMaxLanes));
   CK(h->next_token.ensure(static_cast<size_t>(R) * 8));
   CK(h->logprob_sum.ensure(static_cast<size_t>(R) * 4));
   h->cur_beam = beam;
@@ -806,21 +825,26 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
 // One decode step for the `rows` sequences: embed next_token at state->pos, 6 layers against the KV caches,
 // optional LM head -> h->logits.  Every kernel reads the position / finished flag from device state so the
 // same launch sequence (and CUDA graph) serves every step.
-static int step_layers(gitb200_engine* h, const long long* tokens, const int* src_row, bool lm_head, cudaStream_t st) {
-  const int D = h->D, F = h->F, R = h->cur_rows, nl = h->cfg.dec_layers, beam = h->cur_beam;
-  StepState* state = h->state.as<StepState>();
+static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, const int* src_row, bool lm_head) {
+  const int D = h->D, F = h->F, R = ln_.rows, nl = h->cfg.dec_layers, beam = h->cur_beam;
+  cudaStream_t st = ln_.st;
+  StepState* state = h->state.as<StepState>() + ln_.idx;
   const int* skip = &state->finished;
-  float* xd = h->xd_t.as<float>();
-  bf16* hd = h->hd_t.as<bf16>();
-  float* qkv = h->qkv_t.as<float>();
-  bf16* ctx = h->ctx_t.as<bf16>();
-  float* t = h->t_t.as<float>();
-  bf16* u = h->u_t.as<bf16>();
+  const long long r0 = ln_.row0;
+  float* xd = h->xd_t.as<float>() + r0 * D;
+  bf16* hd = h->hd_t.as<bf16>() + r0 * D;
+  float* qkv = h->qkv_t.as<float>() + r0 * 3 * D;
+  bf16* ctx = h->ctx_t.as<bf16>() + r0 * D;
+  float* t = h->t_t.as<float>() + r0 * D;
+  bf16* u = h->u_t.as<bf16>() + r0 * F;
+  float* logits = h->logits.as<float>() + r0 * h->V;
+  const long long img_off = static_cast<long long>(ln_.b0) * h->cur_M * D;
+  const long long txt_off = r0 * h->T_alloc * D;
   const bool pdl = h->use_pdl;
   // Ordering inside the step: flag chain (greedy; the beam bookkeeping kernels still use grid dependencies).
   const bool chain_on = pdl && h->use_chain && beam == 1;
   ChainSync cs{};
-  cs.counters = chain_on ? h->chain.as<unsigned int>() : nullptr;
+  cs.counters = chain_on ? h->chain.as<unsigned int>() + ln_.idx * 64 : nullptr;
   cs.idx = 0;
   cs.pred_ctas = 0;
   auto next_link = [&](unsigned int ctas_of_this_kernel) {  // call after each launch
@@ -852,16 +876,16 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
     DecLayer& l = h->dec[j];
     TRY(skinny(gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, nullptr, ACT_NONE, qkv, 3 * D, false, 3, skip, pdl)));
     DecAttnParams ap{};
-    ap.qkv = qkv; ap.bqkv = l.bqkv.as<float>(); ap.img_k = img_kv_ptr(h, j, 0); ap.img_v = img_kv_ptr(h, j, 1);
-    ap.txt_k = txt_kv_ptr(h, j, 0); ap.txt_v = txt_kv_ptr(h, j, 1);
-    ap.src_row = src_row; ap.ctx = ctx; ap.B = h->cur_B; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
+    ap.qkv = qkv; ap.bqkv = l.bqkv.as<float>(); ap.img_k = img_kv_ptr(h, j, 0) + img_off; ap.img_v = img_kv_ptr(h, j, 1) + img_off;
+    ap.txt_k = txt_kv_ptr(h, j, 0) + txt_off; ap.txt_v = txt_kv_ptr(h, j, 1) + txt_off;
+    ap.src_row = src_row; ap.ctx = ctx; ap.B = ln_.nb; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
     ap.state = state;
     ap.chunk_rows = h->attn_chunk_rows; ap.box_rows = h->attn_box_rows;
     ap.chain = cs;
     CUtensorMap tk, tv;
-    TRY(get_tmap(h, ap.img_k, static_cast<long long>(h->cur_B) * h->cur_M, D, D, ap.box_rows, &tk, false));
-    TRY(get_tmap(h, ap.img_v, static_cast<long long>(h->cur_B) * h->cur_M, D, D, ap.box_rows, &tv, false));
-    dim3 grid(h->attn_grid);
+    TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
+    TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
+    dim3 grid(std::min(h->attn_grid, ln_.nb * h->cfg.dec_heads));
     if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
@@ -874,9 +898,9 @@ static int step_layers(gitb200_engine* h, const long long* tokens, const int* sr
     TRY(ln(ln_params(t, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, R)));
   }
   if (lm_head)
-    TRY(skinny(gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, h->logits.p, h->V, false, 1, skip, pdl)));
-  h->last_chain_idx = cs.idx;
-  h->last_chain_ctas = cs.pred_ctas;
+    TRY(skinny(gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, logits, h->V, false, 1, skip, pdl)));
+  ln_.chain_idx = cs.idx;
+  ln_.chain_ctas = cs.pred_ctas;
   return 0;
 }
 
@@ -895,8 +919,8 @@ static int set_attn_smem_limit(gitb200_engine* h) {
   h->attn_grid = std::min(items, per_sm * h->num_sms);
   CK(cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
-  CK(h->chain.ensure(256));
-  CK(cudaMemset(h->chain.p, 0, 256));
+  CK(h->chain.ensure(256 * kMaxLanes));
+  CK(cudaMemset(h->chain.p, 0, 256 * kMaxLanes));
   return 0;
 }
 

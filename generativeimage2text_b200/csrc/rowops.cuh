@@ -285,7 +285,8 @@ struct SelectParams {
   long long* next_token;    // [rows] input of the next step
   const long long* forced;  // [rows, max_steps] or null
   StepState* state;
-  float* step_logits;       // optional dump [steps, rows, V]
+  float* step_logits;       // optional dump [steps, rows_total, V]
+  int rows_total, row0;     // this launch covers rows [row0, row0 + rows) of the batch (decode lanes)
   // per-row partial results of the vocabulary slices (grid.x = n_split CTAs per row)
   int n_split;
   float* part_max;          // [rows, n_split]
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
   const int lo = split * chunk;
   const int hi = min(p.V, lo + chunk);
   if (p.step_logits != nullptr) {
-    float* dst = p.step_logits + (static_cast<long long>(step) * p.rows + row) * p.V;
+    float* dst = p.step_logits + (static_cast<long long>(step) * p.rows_total + p.row0 + row) * p.V;
     for (int i = lo + tid; i < hi; i += 256) dst[i] = z[i];
   }
   float m = -INFINITY, ssum = 0.f;
@@ -438,21 +439,33 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
   }
 }
 
-// logprobs / num_valid (reference layers/decoder.py:433-438) and EOS padding of the unused tail.
+// logprobs / num_valid (reference layers/decoder.py:433-438) and EOS padding of the unused tail.  With decode lanes
+// the loop length is that of the slowest lane (the reference stops when ALL rows have ended; rows of a lane that
+// stopped earlier would only have been fed forced EOS steps, which add exactly 0 to their logprob).
+struct LaneRows {
+  int n;
+  int row0[4];
+  int rows[4];
+};
 __global__ void greedy_finalize_kernel(long long* tokens_out, const float* logprob_sum, float* logprobs_out, int rows,
-                                       int max_steps, int prefix_len, int eos, const StepState* st) {
+                                       int max_steps, int prefix_len, int eos, StepState* states, LaneRows lanes) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
-  const int n = st->final_len;
+  int n = 0, empty = 1, n_lane = 0;
+  for (int l = 0; l < lanes.n; ++l) {
+    n = max(n, states[l].final_len);
+    empty &= states[l].empty_caption;
+    if (row >= lanes.row0[l] && row < lanes.row0[l] + lanes.rows[l]) n_lane = states[l].final_len;
+  }
+  for (int i = n_lane; i < max_steps; ++i) tokens_out[static_cast<long long>(row) * max_steps + i] = eos;
   int not_eos = 0, has_eos = 0;
   for (int i = 0; i < n; ++i) {
     const long long t = tokens_out[static_cast<long long>(row) * max_steps + i];
     if (t == eos) has_eos = 1; else ++not_eos;
   }
-  for (int i = n; i < max_steps; ++i) tokens_out[static_cast<long long>(row) * max_steps + i] = eos;
   int num_valid = not_eos + has_eos - prefix_len;
   if (num_valid < 1) num_valid = 1;
-  logprobs_out[row] = st->empty_caption ? logprob_sum[row] : logprob_sum[row] / static_cast<float>(num_valid);
+  logprobs_out[row] = empty ? logprob_sum[row] : logprob_sum[row] / static_cast<float>(num_valid);
 }
 
 }  // namespace gitb200

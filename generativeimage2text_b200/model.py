@@ -140,7 +140,7 @@ class GitB200CaptioningModel(nn.Module):
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
             self._engine, self._engine_device, self._weights_sig = h, dev, None
             import os
-            for opt in ('use_graph', 'use_pdl'):     # debugging switches: GITB200_USE_GRAPH=0 / GITB200_USE_PDL=0
+            for opt in ('use_graph', 'use_pdl', 'use_chain', 'lanes'):   # debugging switches, e.g. GITB200_LANES=1
                 v = os.environ.get('GITB200_' + opt.upper())
                 if v is not None:
                     _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')
@@ -167,6 +167,11 @@ class GitB200CaptioningModel(nn.Module):
             self.release()
         except Exception:
             pass
+
+    def set_engine_option(self, name, value):
+        """Engine switches: 'use_graph', 'use_pdl', 'use_chain' (0/1), 'lanes' (1..4 concurrent decode row groups)."""
+        lib, _ = self._ensure_engine()
+        _lib.check(lib.gitb200_set_option(self._engine, name.encode(), int(value)), self._engine, 'set_option')
 
     def launch_count(self):
         return int(_lib.load().gitb200_launch_count(self._engine)) if self._engine is not None else 0

@@ -236,3 +236,25 @@ def test_generate_host_and_tensor_vs_list_input():
     assert torch.equal(toks[:, :n.value], a['predictions'].cpu())
     # split-K partial sums are accumulated with fp32 atomics: run-to-run order noise ~1e-4 on a logprob
     assert torch.allclose(lps, a['logprobs'].cpu(), atol=2e-3)
+
+
+def test_decode_lanes_match_single_lane():
+    """Batch 32 runs as two concurrent decode lanes of 16 rows; teacher-forced with the single-lane run's tokens the
+    step logits must agree to fp32-atomics noise, and the free-running captions must agree wherever decided."""
+    from generativeimage2text_b200.synthetic import synthetic_state_dict, synthetic_images
+    meta = {'param': {}, 'search': 'greedy', 'max_steps': 16}
+    sd = synthetic_state_dict({}, 3, 'perturbed')
+    img = synthetic_images(32, 0, 77).cuda()
+    m = _model(meta, sd)
+    m.set_engine_option('lanes', 1)
+    a = m({'image': img}, return_step_logits=True)
+    forced = a['predictions'].clone()
+    za = a['step_logits'].clone()
+    m.set_engine_option('lanes', 2)
+    b = m({'image': img}, forced_tokens=forced, return_step_logits=True)
+    torch.cuda.synchronize()
+    err = (b['step_logits'] - za).abs().max().item()
+    print('lanes 2 vs 1: max |dlogit| %.2e, token agreement %.4f' % (err, (b['predictions'] == forced).float().mean().item()))
+    assert err < 5e-3
+    assert (b['predictions'] == forced).float().mean().item() > 0.98
+    assert torch.allclose(a['logprobs'], b['logprobs'], atol=5e-2)
