@@ -22,24 +22,37 @@ namespace gitb200 {
 struct GemmParams {
   int M, N, K;
   int k_splits;
-  int transposed;
+  int transposed;             // epilogue shape / options below select the kernel instantiation on the host
   int atomic;
   int act;
   int out_bf16;
   const float* bias;
-  const float* resid;  // normal mode only, fp32, identity row mapping
+  const float* resid;         // normal mode only, fp32, identity row mapping
   long long ld_resid;
-  void* out[3];
-  long long ldo[3];
-  long long batch_stride[3];  // in rows
+  void* out[3];               // column segments (normal mode): N split into equal seg_n-wide parts
+  long long ldo;              // row pitch of every output segment (elements)
+  long long batch_stride;     // in rows
   int seg_n;                  // segment width (normal mode); N for a single segment
-  int rows_per_batch;         // row map: m -> (m / rpb) * batch_stride[seg] + (m % rpb) + row_offset
+  int rows_per_batch;         // row map: m -> (m / rpb) * batch_stride + (m % rpb) + row_offset
   int row_offset;
   const int* skip;            // device flag: non-zero -> the whole launch is a no-op (finished decode)
   unsigned long long* dbg;    // optional [8] %globaltimer stamps of CTA 0 (profiling aid; null in production)
   int pdl;                    // launched with programmatic dependent launch: prefetch weights, then griddep_wait()
   ChainSync chain;            // flag-based ordering inside the decode step (see ptx.cuh); counters == null: off
 };
+
+// Epilogue variants are compile-time (the runtime-flag version spent ~700 warp instructions per 32x32 chunk,
+// which made every K=768 GEMM of the encoder epilogue-issue bound).
+constexpr int EPI_TRANSPOSED = 1, EPI_BF16 = 2, EPI_RESID = 4, EPI_ATOMIC = 8, EPI_ACT_SHIFT = 4;
+constexpr int epi_code(bool transposed, bool bf16, bool resid, bool atomic, int act) {
+  return (transposed ? EPI_TRANSPOSED : 0) | (bf16 ? EPI_BF16 : 0) | (resid ? EPI_RESID : 0) | (atomic ? EPI_ATOMIC : 0) |
+         (act << EPI_ACT_SHIFT);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+  return apply_act(x, ACT);  // ACT is a constant: the branches fold away
+}
 
 template <int BN>
 struct GemmCfg {
@@ -63,17 +76,23 @@ struct GemmCfg {
   static_assert(STAGES >= 3, "pipeline depth");
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmParams p) {
   using C = GemmCfg<BN>;
+  constexpr bool kTransposed = (EPI & EPI_TRANSPOSED) != 0;
+  constexpr bool kBf16 = (EPI & EPI_BF16) != 0;
+  constexpr bool kResid = (EPI & EPI_RESID) != 0;
+  constexpr bool kAtomic = (EPI & EPI_ATOMIC) != 0;
+  constexpr int kAct = EPI >> EPI_ACT_SHIFT;
   if (p.pdl) griddep_launch();
   if (p.pdl) tl_mark(100000 + 1000 + static_cast<int>(gridDim.x));
   // `skip` (decode finished) only changes between steps, which are separated by full dependencies
   if ((!p.pdl || p.chain.counters != nullptr) && p.skip != nullptr && *p.skip != 0) return;  // uniform over the grid
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // keep the shared-memory provenance of the pointer (plain pointer arithmetic) so staging accesses compile to LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
   uint8_t* sStage = smem + C::STAGES * C::STAGE_BYTES;
@@ -112,30 +131,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();
-  // PDL: everything above overlapped the predecessor kernel. The producer additionally prefetches the weight
-  // tiles (which no kernel writes) before it waits; every other thread waits here.
-  const bool chained = p.chain.counters != nullptr;
-  if (chained) {
-    // weights are never written during decoding: request the first tiles before waiting for the predecessor
-    if (warp == 0 && lane == 0 && p.transposed && static_cast<int>(blockIdx.x) < ((p.M + C::BM - 1) / C::BM) * ((p.N + BN - 1) / BN) * p.k_splits) {
-      const int mt = (p.M + C::BM - 1) / C::BM, nt = (p.N + BN - 1) / BN;
-      const int kbt = (p.K + C::BK - 1) / C::BK, kbp = (kbt + p.k_splits - 1) / p.k_splits;
-      const int tile = blockIdx.x;
-      const int split = tile / (mt * nt);
-      const int m_blk = (tile - split * mt * nt) / nt;
-      const int kb0 = split * kbp;
-      const int kb1 = min(kbt, kb0 + kbp);
-      const int npre = min(C::STAGES, kb1 - kb0);
-      for (int i = 0; i < npre; ++i) {
-        mbar_arrive_expect_tx(&full[i], C::STAGE_BYTES);
-        tma_load_2d(sA + i * C::A_BYTES, &tmA, &full[i], (kb0 + i) * C::BK, m_blk * C::BM);
-      }
-    }
-    chain_wait(p.chain);
-  } else if (p.pdl && !(warp == 0 && lane == 0)) {
-    griddep_wait();
-  }
-  if (p.pdl) tl_mark(1000 + static_cast<int>(gridDim.x));
 
   const int m_tiles = (p.M + C::BM - 1) / C::BM;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -144,34 +139,31 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int mn_tiles = m_tiles * n_tiles;
   const int num_tiles = mn_tiles * p.k_splits;
 
+  // PDL / chain: everything above overlapped the predecessor kernel. In the swap-AB shape the A operand is a
+  // weight matrix that no kernel writes: its first tiles are requested before waiting for the predecessor.
+  const bool chained = p.chain.counters != nullptr;
+  int npre = 0;
+  if (kTransposed && p.pdl && static_cast<int>(blockIdx.x) < num_tiles) {
+    const int split = static_cast<int>(blockIdx.x) / mn_tiles;
+    const int kb0 = split * kb_per;
+    npre = min(C::STAGES, min(kb_total, kb0 + kb_per) - kb0);
+    if (warp == 0 && lane == 0) {
+      const int m_blk = (static_cast<int>(blockIdx.x) - split * mn_tiles) / n_tiles;
+      for (int i = 0; i < npre; ++i) {
+        mbar_arrive_expect_tx(&full[i], C::STAGE_BYTES);
+        tma_load_2d(sA + i * C::A_BYTES, &tmA, &full[i], (kb0 + i) * C::BK, m_blk * C::BM);
+      }
+    }
+  }
+  if (chained) chain_wait(p.chain);
+  else if (p.pdl) griddep_wait();
+  if (p.pdl) tl_mark(1000 + static_cast<int>(gridDim.x));
+
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int npre = 0;  // k-blocks of the first tile whose weight tile was requested before the dependency wait
-      if (chained) {
-        if (p.transposed && static_cast<int>(blockIdx.x) < num_tiles) {
-          const int split = static_cast<int>(blockIdx.x) / mn_tiles;
-          const int kb0 = split * kb_per;
-          npre = min(C::STAGES, min(kb_total, kb0 + kb_per) - kb0);
-        }
-      } else if (p.pdl) {
-        if (p.transposed && static_cast<int>(blockIdx.x) < num_tiles) {
-          const int tile = blockIdx.x;
-          const int split = tile / mn_tiles;
-          const int rem = tile - split * mn_tiles;
-          const int m_blk = rem / n_tiles;
-          const int kb0 = split * kb_per;
-          const int kb1 = min(kb_total, kb0 + kb_per);
-          npre = min(C::STAGES, kb1 - kb0);
-          for (int i = 0; i < npre; ++i) {
-            mbar_arrive_expect_tx(&full[i], C::STAGE_BYTES);
-            tma_load_2d(sA + i * C::A_BYTES, &tmA, &full[i], (kb0 + i) * C::BK, m_blk * C::BM);
-          }
-        }
-        griddep_wait();
-      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / mn_tiles;
         const int rem = tile - split * mn_tiles;
@@ -238,13 +230,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= 4) {
     // ------------------------------ epilogue ----------------------------------
     // 8 warps: warp w reads TMEM lanes 32*(w%4).. (hardware restriction) and the 32-column chunks
-    // c == (w-4)/4 (mod 2).  Normal mode transposes each 32x32 fp32 chunk through a per-warp swizzled
-    // staging buffer so that global loads (residual) and stores are fully coalesced 128-byte rows.
+    // c == (w-4)/4 (mod 2).  Every 32x32 fp32 chunk is transposed through a per-warp swizzled staging buffer so
+    // that each lane ends up with 4 consecutive output elements of one row: coalesced 128-bit accesses.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    const bool store_ok = !(p.pdl && !chained && p.skip != nullptr && *p.skip != 0);  // finished decode: compute, do not store
+    const bool store_ok = !(p.pdl && !chained && p.skip != nullptr && *p.skip != 0);  // finished decode: no stores
     uint8_t* stg = sStage + (warp - 4) * (32 * 128);
-    const uint32_t stg_u32 = smem_u32(stg);
+    const int c4 = lane & 7;
+    const int rsub = lane >> 3;
+    const bool single_seg = p.seg_n >= p.N;
     int accum = 0;
     uint32_t accum_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -252,11 +246,25 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int rem = tile - split * mn_tiles;
       const int m_blk = rem / n_tiles;
       const int n_blk = rem - m_blk * n_tiles;
+      const int row0 = m_blk * C::BM + q * 32;  // first tile row of this warp
+      // ---- per-tile row bookkeeping (normal mode): output row offsets of this lane's 8 rows ----
+      long long ooff[8];
+      uint32_t okmask = 0;
+      if (!kTransposed) {
+        int bq = (row0 + rsub) / p.rows_per_batch;
+        int sq = (row0 + rsub) - bq * p.rows_per_batch;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (row0 + it * 4 + rsub < p.M && store_ok) okmask |= 1u << it;
+          ooff[it] = (static_cast<long long>(bq) * p.batch_stride + sq + p.row_offset) * p.ldo;
+          sq += 4;
+          while (sq >= p.rows_per_batch) { sq -= p.rows_per_batch; ++bq; }
+        }
+      }
       mbar_wait(&tfull[accum], accum_phase);
       tc_fence_after();
       if (dbg && tile == 0 && warp == 4 && lane == 0) p.dbg[4] = globaltimer_ns();
       if (p.pdl && tile == static_cast<int>(blockIdx.x) && warp == 4 && lane == 0) tl_mark_one(400000 + 1000 + static_cast<int>(gridDim.x));
-      const int row0 = m_blk * C::BM + q * 32;  // first row of this warp
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int n0 = n_blk * BN + c * 32;
@@ -264,20 +272,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN + c * 32, r);
         tmem_ld_wait();
-        if (!p.transposed) {
+        if (!kTransposed) {
           // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
           // phase 2: 8 lanes per row (4 columns each), 4 rows per instruction
-          const int c4 = lane & 7;
-          const int rsub = lane >> 3;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + c4);
-          const int seg = n0 / p.seg_n;
+          int seg = 0;
+          if (!single_seg) seg = n0 / p.seg_n;
           const int nn = n0 - seg * p.seg_n + c4 * 4;
           float4 v[8];
 #pragma unroll
@@ -285,42 +290,35 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int rr = it * 4 + rsub;
             v[it] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
           }
-          if (p.resid != nullptr) {
+          if (kResid) {
+            const float* rbase = p.resid + static_cast<long long>(row0 + rsub) * p.ld_resid + n0 + c4 * 4;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const int row = row0 + it * 4 + rsub;
-              if (row < p.M) {
-                const float4 r4 = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ld_resid + n0 + c4 * 4);
+              if (okmask & (1u << it)) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rbase + static_cast<long long>(it) * 4 * p.ld_resid);
                 v[it].x += r4.x; v[it].y += r4.y; v[it].z += r4.z; v[it].w += r4.w;
               }
             }
           }
-          // row map of the first row of this lane; later rows advance by 4 and wrap at the batch boundary
-          int bq = (row0 + rsub) / p.rows_per_batch;
-          int sq = (row0 + rsub) - bq * p.rows_per_batch;
+          uint8_t* obase = reinterpret_cast<uint8_t*>(p.out[seg]) + static_cast<long long>(nn) * (kBf16 ? 2 : 4);
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int row = row0 + it * 4 + rsub;
             float4 o = v[it];
             // bias and activation come before the residual in every caller that uses both (resid => act none)
             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-            if (p.act != ACT_NONE) {
-              o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
-              o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
+            if (kAct != ACT_NONE) {
+              o.x = act_ct<kAct>(o.x); o.y = act_ct<kAct>(o.y); o.z = act_ct<kAct>(o.z); o.w = act_ct<kAct>(o.w);
             }
-            if (row < p.M && store_ok) {
-              const long long orow = static_cast<long long>(bq) * p.batch_stride[seg] + sq + p.row_offset;
-              if (p.out_bf16) {
+            if (okmask & (1u << it)) {
+              if (kBf16) {
                 uint2 pk;
                 pk.x = pack_bf16(o.x, o.y);
                 pk.y = pack_bf16(o.z, o.w);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + orow * p.ldo[seg] + nn) = pk;
+                *reinterpret_cast<uint2*>(obase + ooff[it] * 2) = pk;
               } else {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + orow * p.ldo[seg] + nn) = o;
+                *reinterpret_cast<float4*>(obase + ooff[it] * 4) = o;
               }
             }
-            sq += 4;
-            while (sq >= p.rows_per_batch) { sq -= p.rows_per_batch; ++bq; }
           }
           __syncwarp();
         } else {
@@ -331,8 +329,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < 32; ++j)
             *reinterpret_cast<uint32_t*>(stg + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + ((lane & 3) << 2)) = r[j];
           __syncwarp();
-          const int c4 = lane & 7;
-          const int rsub = lane >> 3;
           const int f0 = row0 + c4 * 4;  // first of this lane's 4 features
           const bool full4 = (f0 + 3) < p.M;
           float bv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -347,13 +343,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int arow = n0 + rr;
             const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
             float v[4] = {t4.x + bv[0], t4.y + bv[1], t4.z + bv[2], t4.w + bv[3]};
-            if (p.act != ACT_NONE) {
+            if (kAct != ACT_NONE) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], p.act);
+              for (int e = 0; e < 4; ++e) v[e] = act_ct<kAct>(v[e]);
             }
             if (arow < p.N && store_ok && f0 < p.M) {
-              const long long off = static_cast<long long>(arow) * p.ldo[0] + f0;
-              if (p.atomic) {
+              const long long off = static_cast<long long>(arow) * p.ldo + f0;
+              if (kAtomic) {
                 float* dst = reinterpret_cast<float*>(p.out[0]) + off;
                 if (full4) {
                   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
@@ -361,9 +357,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   for (int e = 0; e < 4; ++e)
                     if (f0 + e < p.M) atomicAdd(dst + e, v[e]);
                 }
-              } else if (p.out_bf16) {
+              } else if (kBf16) {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[0]) + off;
-                if (full4 && (p.ldo[0] & 3) == 0) {
+                if (full4 && (p.ldo & 3) == 0) {
                   uint2 pk;
                   pk.x = pack_bf16(v[0], v[1]);
                   pk.y = pack_bf16(v[2], v[3]);
@@ -374,9 +370,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               } else {
                 float* dst = reinterpret_cast<float*>(p.out[0]) + off;
-                if (full4 && (p.ldo[0] & 3) == 0) {
+                if (full4 && (p.ldo & 3) == 0) {
                   *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                } else if (full4 && (p.ldo[0] & 1) == 0) {
+                } else if (full4 && (p.ldo & 1) == 0) {
                   *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
                   *reinterpret_cast<float2*>(dst + 2) = make_float2(v[2], v[3]);
                 } else {

@@ -134,7 +134,7 @@ struct gitb200_engine {
   cudaEvent_t own_event = nullptr;
   // decode lanes: the greedy batch is split into independent row groups whose (latency-bound) kernel chains run
   // concurrently on separate streams -- forked and joined inside the captured step graph
-  int lanes_opt = 2;
+  int lanes_opt = 1;   // measured: the chains are latency bound, concurrent lanes do not shorten a step (kept as an option)
   cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -250,12 +250,12 @@ struct GemmCall {
   int bn = 0;               // 0 = heuristic
 };
 
-template <int BN>
-static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
+template <int BN, int EPI>
+static int launch_gemm_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
   using C = GemmCfg<BN>;
   static bool attr_set[64] = {false};
   if (!attr_set[h->device & 63]) {
-    CK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set[h->device & 63] = true;
   }
   CUtensorMap ta, tb;
@@ -266,30 +266,49 @@ static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st)
   const int tiles = m_tiles * n_tiles * c.p.k_splits;
   const int grid = tiles < h->num_sms ? tiles : h->num_sms;
   h->last_gemm_grid = grid;
-  CK(launch_k(c.p.pdl != 0, gemm_bf16_tcgen05<BN>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
+  CK(launch_k(c.p.pdl != 0, gemm_bf16_tcgen05<BN, EPI>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
   CKL(h, "gemm_bf16_tcgen05");
   return 0;
 }
 
-static int pick_bn(const gitb200_engine* h, int M, int N, bool transposed) {
-  if (transposed) return N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  const int m_tiles = (M + 127) / 128;
-  int best = 256;
-  double best_cost = 1e30;
-  const int cands[3] = {256, 192, 128};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (N % bn != 0 && N > bn) continue;
-    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
-    const long long waves = (tiles + h->num_sms - 1) / h->num_sms;
-    // per-tile cost ~ bn (MMA time) + fixed overhead; narrower tiles pay relatively more smem traffic
-    const double cost = static_cast<double>(waves) * (bn + 24.0) * (bn == 128 ? 1.08 : 1.0);
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+// The epilogue variants the hot path uses (each is its own kernel instantiation).
+template <int BN>
+static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
+  const GemmParams& p = c.p;
+  const int code = epi_code(p.transposed != 0, p.out_bf16 != 0, p.resid != nullptr, p.atomic != 0, p.act);
+  if constexpr (BN == 192 || BN == 256 || BN == 128) {
+    switch (code) {
+      case epi_code(false, true, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, false, true, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, false, true, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, false, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, false, false, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_QUICKGELU): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_GELU_ERF): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF)>(h, c, st);
+      default: break;
     }
   }
-  return best;
+  if constexpr (BN == 64 || BN == 128 || BN == 256) {
+    switch (code) {
+      case epi_code(true, false, false, true, ACT_NONE): return launch_gemm_inst<BN, epi_code(true, false, false, true, ACT_NONE)>(h, c, st);
+      case epi_code(true, false, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(true, false, false, false, ACT_NONE)>(h, c, st);
+      case epi_code(true, true, false, false, ACT_GELU_ERF): return launch_gemm_inst<BN, epi_code(true, true, false, false, ACT_GELU_ERF)>(h, c, st);
+      default: break;
+    }
+  }
+  return fail(h, "gemm: epilogue combination not instantiated (transposed=%d bf16=%d resid=%d atomic=%d act=%d bn=%d)",
+              p.transposed, p.out_bf16, p.resid != nullptr, p.atomic, p.act, BN);
+}
+
+static int pick_bn(const gitb200_engine* h, int M, int N, bool transposed) {
+  if (transposed) return N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  // Measured on B200 (tools/gemm_sweep.py, M = 12608): wide outputs (N = 2304 / 3072) run best with 128x256 tiles
+  // (fewest operand bytes per FLOP through L2/shared memory); N = 768 with 128x192 tiles (4 column tiles: less
+  // wave quantisation than 3 x 256 at 99 row tiles over 148 SMs).
+  (void)h; (void)M;
+  if (N % 256 == 0 && N >= 1024) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  return N > 192 ? 256 : (N > 128 ? 192 : 128);
 }
 
 static int launch_gemm(gitb200_engine* h, GemmCall c, cudaStream_t st) {
@@ -304,7 +323,7 @@ static int launch_gemm(gitb200_engine* h, GemmCall c, cudaStream_t st) {
   if (p.seg_n <= 0) p.seg_n = p.N;
   if (p.rows_per_batch <= 0) {
     p.rows_per_batch = p.M;
-    for (int i = 0; i < 3; ++i) p.batch_stride[i] = p.M;
+    p.batch_stride = p.M;
   }
   if (!p.transposed && (p.N % 32 != 0 || p.seg_n % 32 != 0))
     return fail(h, "gemm: N and segment width must be multiples of 32 (N=%d seg=%d)", p.N, p.seg_n);
@@ -327,7 +346,7 @@ static GemmCall gemm_plain(const bf16* A, long long lda, const bf16* W, long lon
   c.A = A; c.lda = lda; c.B = W; c.ldb = ldw;
   c.p.M = M; c.p.N = N; c.p.K = K; c.p.k_splits = 1;
   c.p.bias = bias; c.p.act = act; c.p.resid = resid; c.p.ld_resid = N;
-  c.p.out[0] = out; c.p.ldo[0] = N; c.p.out_bf16 = out_bf16 ? 1 : 0;
+  c.p.out[0] = out; c.p.ldo = N; c.p.out_bf16 = out_bf16 ? 1 : 0;
   c.p.seg_n = N;
   return c;
 }
@@ -340,7 +359,7 @@ static GemmCall gemm_skinny(const bf16* X, long long ldx, const bf16* W, long lo
   c.p.M = feats; c.p.N = rows; c.p.K = K; c.p.k_splits = k_splits;
   c.p.transposed = 1; c.p.atomic = k_splits > 1 ? 1 : 0;
   c.p.bias = bias; c.p.act = act;
-  c.p.out[0] = out; c.p.ldo[0] = ldo; c.p.out_bf16 = out_bf16 ? 1 : 0;
+  c.p.out[0] = out; c.p.ldo = ldo; c.p.out_bf16 = out_bf16 ? 1 : 0;
   c.p.skip = skip;
   c.p.pdl = pdl ? 1 : 0;
   return c;
@@ -703,7 +722,7 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
     CKL(h, "im2col_patch_kernel");
     GemmCall c = gemm_plain(u, Kp, h->w_patch.as<bf16>(), Kp, NI * g * g, d, Kp, nullptr, ACT_NONE, nullptr, x, false);
     c.p.rows_per_batch = g * g;
-    c.p.batch_stride[0] = L;
+    c.p.batch_stride = L;
     c.p.row_offset = 1;
     TRY(launch_gemm(h, c, st));
     const int gridr = static_cast<int>((Me + 7) / 8);
@@ -805,7 +824,7 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
     GemmCall c = gemm_plain(hd, D, l.wqkv.as<bf16>(), D, static_cast<int>(rows), 3 * D, D, l.bqkv.as<float>(), ACT_NONE, nullptr, q, true);
     c.p.seg_n = D;
     c.p.out[0] = q; c.p.out[1] = img_kv_ptr(h, j, 0); c.p.out[2] = img_kv_ptr(h, j, 1);
-    c.p.ldo[0] = c.p.ldo[1] = c.p.ldo[2] = D;
+    c.p.ldo = D;
     TRY(launch_gemm(h, c, st));
     if (j + 1 == nl) break;  // image rows of the last layer are never read (text rows only need their K/V)
     AttnParams ap{};
