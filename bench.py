@@ -132,6 +132,8 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true')
+    ap.add_argument('--ncu-range', action='store_true',
+                    help='bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)')
     args = ap.parse_args()
     rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
     if args.impl == 'reference':
@@ -187,11 +189,15 @@ def main():
             sampler.start()
         launches0 = model.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.ncu_range:
+            torch.cuda.profiler.start()
         e0.record(stream)
         for _ in range(args.steps):
             toks = one_step_device()
         e1.record(stream)
         barrier()
+        if args.ncu_range:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         launches = model.launch_count() - launches0
         assert toks.shape[0] == n_total and toks.shape[1] == MAX_STEPS
