@@ -48,34 +48,59 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (per launch) from the committed
+    `ncu --set full` capture (profiles/prof_gemm_r01.md): 24.1 MB read + 24.8 MB write."""
+    p = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get('dram_bytes_per_launch')
+    return None
+
+
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line), streamed with
+    `-lms` so that even a sub-second region gets several samples."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
         self.reasons = set()
-        self.stop_flag = False
         self.max_mhz = None
+        self.proc = None
+        self.stop_flag = False
 
     def run(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(',')]
+                if len(f) < 6:
+                    continue
+                try:
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                except ValueError:
+                    continue
                 for n, v in zip(names, f[2:]):
                     if v.lower().startswith('active'):
                         self.reasons.add(n)
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.1)
 
     def summary(self):
         s = sorted(self.samples)
@@ -238,7 +263,7 @@ def main():
     ms_e2e = t.item()
     e2e_value = n_total * args.steps / (ms_e2e / 1e3)
     if rank == 0:
-        sampler.stop_flag = True
+        sampler.stop()
         sampler.join(timeout=2)
 
     # ---------------- roofline of the dominant kernel, measured live ----------------
@@ -275,7 +300,7 @@ def main():
         achieved = flops / (avg_ms / 1e3) / 1e12
         roofline = {'kernel': 'gemm_bf16_tcgen05<BN> (ViT mlp.c_fc shape %dx%dx%d, bias+QuickGELU epilogue)' % (M, N, K),
                     'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                    'frac': achieved / peaks['bf16_tflops'], 'traffic': None, 'avg_launch_ms': avg_ms,
+                    'frac': achieved / peaks['bf16_tflops'], 'traffic': ncu_traffic(), 'avg_launch_ms': avg_ms,
                     'peak_source': peaks['source'] + ', burst bf16 figure (kernel timed alone, L2 flushed between launches)'}
         extra['whole_step'] = {
             'algorithmic_tflop_per_step': 58.1e9 * B / 1e12,

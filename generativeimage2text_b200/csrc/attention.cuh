@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NW * 32) flash_attn_kernel(const AttnParams p)
 // ------------------------------------------------------------------------------------------------
 struct DecAttnParams {
   float* qkv;                      // [R, 3*D] fp32 (q | k | v): split-K accumulation buffer, zeroed after reading
-  const float* bqkv;               // [3*D] bias, added here
+  const float* bqkv;               // [3*D] bias added here and qkv re-zeroed (split-K producer); null: qkv is final
   const __nv_bfloat16* img_k;      // [B, M, D]
   const __nv_bfloat16* img_v;
   __nv_bfloat16* txt_k;            // [R, T_alloc, D]
@@ -331,20 +331,23 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     for (int qi = 0; qi < NQ; ++qi) {
       const int r = b * NQ + qi;
       float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
-      const float* bias = p.bqkv + h * 64;
+      const float* bias = (p.bqkv != nullptr ? p.bqkv : p.qkv) + h * 64;  // never dereferenced when bqkv == null
       const bool have = (NQ == 1) && (k < kPre);
+      const bool acc_mode = p.bqkv != nullptr;
       if (tid < 64) {
         const float qv = have ? pre_a[k < kPre ? k : 0] : __ldcg(row + tid);
         const float kv = have ? pre_b[k < kPre ? k : 0] : __ldcg(row + D + tid);
-        q_s[qi][tid] = (qv + bias[tid]) * 0.125f;
-        p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(kv + bias[D + tid]);
-        row[tid] = 0.f;
-        row[D + tid] = 0.f;
+        q_s[qi][tid] = (qv + (acc_mode ? bias[tid] : 0.f)) * 0.125f;
+        p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(kv + (acc_mode ? bias[D + tid] : 0.f));
+        if (acc_mode) {
+          row[tid] = 0.f;
+          row[D + tid] = 0.f;
+        }
       } else {
         const int d = tid - 64;
         const float vv = have ? pre_a[k < kPre ? k : 0] : __ldcg(row + 2 * D + d);
-        p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(vv + bias[2 * D + d]);
-        row[2 * D + d] = 0.f;
+        p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(vv + (acc_mode ? bias[2 * D + d] : 0.f));
+        if (acc_mode) row[2 * D + d] = 0.f;
       }
     }
     __syncthreads();

@@ -81,8 +81,8 @@ __device__ __forceinline__ void chain_wait(const ChainSync& c) {
 }
 // thread 0, after a __syncthreads() that follows the CTA's last global write
 __device__ __forceinline__ void chain_signal_thread0(const ChainSync& c) {
-  __threadfence();
-  atomicAdd(c.counters + c.idx, 1u);
+  // release-RMW: orders this thread's (and, through the preceding bar.sync, the CTA's) prior writes before the count
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.counters + c.idx), "r"(1u) : "memory");
 }
 __device__ __forceinline__ void chain_signal(const ChainSync& c) {
   if (c.counters != nullptr) {

@@ -38,7 +38,9 @@ struct LnParams {
   ChainSync chain;       // decode-step flag ordering (counters == null: plain / PDL ordering)
 };
 
-template <int D>
+// PRE: fetch gamma / beta / bias before the dependency wait (decode chain: hides one L2 round trip; costs registers,
+// so the big encoder LayerNorms use PRE = false).
+template <int D, bool PRE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   static_assert(D % 128 == 0, "D");
   constexpr int NV = D / 128;
@@ -46,12 +48,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   tl_mark(100002);
   const int lane = threadIdx.x & 31;
   // parameters are constants: fetch them before the dependency wait
-  float4 gam[NV], bet[NV], bia[NV];
+  float4 gam[PRE ? NV : 1], bet[PRE ? NV : 1], bia[PRE ? NV : 1];
+  if (PRE) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    gam[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + i * 32 + lane);
-    bet[i] = __ldg(reinterpret_cast<const float4*>(p.beta) + i * 32 + lane);
-    bia[i] = (p.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.bias) + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV; ++i) {
+      gam[i] = __ldg(reinterpret_cast<const float4*>(p.gamma) + i * 32 + lane);
+      bet[i] = __ldg(reinterpret_cast<const float4*>(p.beta) + i * 32 + lane);
+      bia[i] = (p.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.bias) + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   const bool chained = p.chain.counters != nullptr;
   if (chained) {
@@ -84,9 +88,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) zp[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (PRE) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i].x += bia[i].x; v[i].y += bia[i].y; v[i].z += bia[i].z; v[i].w += bia[i].w;
+    for (int i = 0; i < NV; ++i) {
+      v[i].x += bia[i].x; v[i].y += bia[i].y; v[i].z += bia[i].z; v[i].w += bia[i].w;
+    }
+  } else if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + i * 32 + lane);
+      v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+    }
   }
   float s = 0.f;
 #pragma unroll
@@ -111,8 +123,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const float4 g = gam[i];
-    const float4 b = bet[i];
+    const float4 g = PRE ? gam[i] : __ldg(reinterpret_cast<const float4*>(p.gamma) + i * 32 + lane);
+    const float4 b = PRE ? bet[i] : __ldg(reinterpret_cast<const float4*>(p.beta) + i * 32 + lane);
     float4 o;
     o.x = (v[i].x - mean) * rstd * g.x + b.x;
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
