@@ -29,6 +29,7 @@
 #include "../../include/gitb200.h"
 #include "attention.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "ptx.cuh"
 #include "rowops.cuh"
 #include "search.cuh"
@@ -101,6 +102,7 @@ struct gitb200_engine {
   // decode GEMMs through skinny.cuh (mma.sync, fewer dependent hops per CTA) instead of swap-AB tcgen05. Measured on
   // B200 (bench.py, 10 steps): 18.89 ms/step lean vs 18.09 ms tcgen05 -> off by default, kept for comparison.
   bool use_lean = false;
+  bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
 
   // derived geometry
   int g = 0, L = 0, Kpatch = 0, Kp = 0, d = 0, D = 0, F = 0, V = 0;
@@ -275,6 +277,41 @@ static int launch_gemm_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t s
   return 0;
 }
 
+template <int BN, int EPI>
+static int launch_gemm2_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
+  using C = Gemm2Cfg<BN>;
+  static bool attr_set[64] = {false};
+  if (!attr_set[h->device & 63]) {
+    CK(cudaFuncSetAttribute(gemm2_bf16_tcgen05<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set[h->device & 63] = true;
+  }
+  CUtensorMap ta, tb;
+  TRY(get_tmap(h, c.A, c.p.M, c.p.K, c.lda, 128, &ta));
+  TRY(get_tmap(h, c.B, c.p.N, c.p.K, c.ldb, BN / 2, &tb));
+  const int m_tiles = (c.p.M + 255) / 256;
+  const int n_tiles = (c.p.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int pairs = std::min(tiles, h->num_sms / 2);
+  h->last_gemm_grid = 2 * pairs;
+  CK(launch_k(false, gemm2_bf16_tcgen05<BN, EPI>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
+  CKL(h, "gemm2_bf16_tcgen05");
+  return 0;
+}
+template <int BN>
+static int launch_gemm2_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
+  const GemmParams& p = c.p;
+  const int code = epi_code(false, p.out_bf16 != 0, p.resid != nullptr, false, p.act);
+  switch (code) {
+    case epi_code(false, true, false, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_NONE)>(h, c, st);
+    case epi_code(false, false, true, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, false, true, false, ACT_NONE)>(h, c, st);
+    case epi_code(false, false, false, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, false, false, false, ACT_NONE)>(h, c, st);
+    case epi_code(false, true, false, false, ACT_QUICKGELU): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU)>(h, c, st);
+    case epi_code(false, true, false, false, ACT_GELU_ERF): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF)>(h, c, st);
+    default: break;
+  }
+  return fail(h, "gemm2: epilogue combination not instantiated");
+}
+
 // The epilogue variants the hot path uses (each is its own kernel instantiation).
 template <int BN>
 static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
@@ -333,7 +370,22 @@ static int launch_gemm(gitb200_engine* h, GemmCall c, cudaStream_t st) {
     return fail(h, "gemm: N and segment width must be multiples of 32 (N=%d seg=%d)", p.N, p.seg_n);
   if (p.atomic && !p.transposed) return fail(h, "gemm: atomic accumulation is only implemented for the transposed epilogue");
   if (p.k_splits > 1 && !p.atomic) return fail(h, "gemm: k_splits > 1 needs the atomic epilogue");
-  const int bn = c.bn > 0 ? c.bn : pick_bn(h, p.M, p.N, p.transposed != 0);
+  int bn = c.bn > 0 ? c.bn : pick_bn(h, p.M, p.N, p.transposed != 0);
+  // 2-CTA (cta_group::2) kernel: explicit request (bn = 1000 + BN, unit tests) or engine option for the big GEMMs
+  // Measured (tools/gemm_sweep.py, M = 12608): pairs win on wide outputs (+7-10 %) and on K = 3072 (+11 %); the
+  // K = N = 768 out-projection is epilogue bound and stays on 1-CTA 128x192 tiles.
+  if (bn < 1000 && h->use_2cta && !p.transposed && p.k_splits == 1 && p.M >= 2048) {
+    if (p.N % 256 == 0 && p.N >= 1024) bn = 1256;
+    else if (p.N % 192 == 0 && p.K >= 1536) bn = 1192;
+  }
+  if (bn >= 1000) {
+    if (p.transposed || p.k_splits != 1) return fail(h, "gemm2: normal epilogue, no split-K");
+    switch (bn - 1000) {
+      case 256: return launch_gemm2_bn<256>(h, c, st);
+      case 192: return launch_gemm2_bn<192>(h, c, st);
+      default: return fail(h, "gemm2: unsupported tile width %d", bn - 1000);
+    }
+  }
   switch (bn) {
     case 64: return launch_gemm_bn<64>(h, c, st);
     case 128: return launch_gemm_bn<128>(h, c, st);
@@ -481,6 +533,7 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
   if (strcmp(name, "use_lean") == 0) { h->use_lean = value != 0; return 0; }
+  if (strcmp(name, "use_2cta") == 0) { h->use_2cta = value != 0; return 0; }
   if (strcmp(name, "lanes") == 0) { h->lanes_opt = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : static_cast<int>(value)); return 0; }
   return fail(h, "unknown option %s", name);
 }

@@ -140,7 +140,7 @@ class GitB200CaptioningModel(nn.Module):
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
             self._engine, self._engine_device, self._weights_sig = h, dev, None
             import os
-            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'lanes'):   # debugging switches, e.g. GITB200_LANES=1
+            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'lanes'):   # debugging switches, e.g. GITB200_LANES=1
                 v = os.environ.get('GITB200_' + opt.upper())
                 if v is not None:
                     _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')

@@ -64,6 +64,24 @@ def test_gemm_plain(M, N, K, bn):
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize('M,N,K,bn,act,out_bf16,use_resid', [
+    (256, 256, 64, 1256, 0, False, False),     # one pair, one tile, one k-block
+    (512, 512, 512, 1256, 0, True, False),     # several tiles, ring wrap-around
+    (1000, 768, 768, 1192, 0, False, True),    # M tail, 192-wide tiles, residual epilogue
+    (12608, 3072, 768, 1256, 1, True, False),  # ViT c_fc: persistent pairs, TMEM double buffering
+    (12608, 768, 3072, 1192, 0, False, True),  # ViT c_proj
+])
+def test_gemm_2cta(M, N, K, bn, act, out_bf16, use_resid):
+    """cta_group::2 kernel (gemm2.cuh): CTA pairs computing 256 x BN tiles."""
+    a, w = _rand((M, K), 1.0, 41), _rand((N, K), 0.05, 42)
+    bias = _rand((N,), 0.5, 43, torch.float32)
+    resid = _rand((M, N), 1.0, 44, torch.float32) if use_resid else None
+    out = _gemm(a, w, bias, resid, act, out_bf16, False, 1, bn)
+    ref = _ref_gemm(a, w, bias, resid, act)
+    tol = 3e-2 if out_bf16 else 2e-3
+    assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize('act,out_bf16,use_resid', [(0, False, True), (1, True, False), (2, True, False), (0, True, False)])
 def test_gemm_epilogues(act, out_bf16, use_resid):
     M, N, K = 777, 1536, 768

@@ -40,19 +40,23 @@ def bench(M, N, K, act=0, out_bf16=1, resid=False, transposed=0, splits=1, bn=0,
 
 if __name__ == '__main__':
     M = 64 * 197
-    print('--- encoder shapes')
-    for bn in (128, 192, 256):
+    print('--- encoder shapes: 1-CTA (bn) vs 2-CTA pairs (bn = 1000 + BN)')
+    for bn in (256, 1256):
         bench(M, 3072, 768, act=1, bn=bn)
-    bench(M, 3072, 768, act=0, bn=256)
-    bench(M, 3072, 768, act=0, out_bf16=0, bn=256)
-    for bn in (128, 192, 256):
+    for bn in (256, 1256):
+        bench(M, 3072, 768, act=0, bn=bn)
+    for bn in (192, 1192, 256, 1256):
         bench(M, 768, 3072, act=0, out_bf16=0, resid=True, bn=bn)
-    for bn in (128, 192, 256):
+    for bn in (256, 1256):
         bench(M, 2304, 768, bn=bn)
-    for bn in (128, 192, 256):
+    for bn in (192, 1192, 1256):
         bench(M, 768, 768, out_bf16=0, resid=True, bn=bn)
+    for bn in (256, 1256):
+        bench(M, 3072, 768, act=2, bn=bn)
     bench(8192, 8192, 8192, bn=256, iters=3)
-    bench(8192, 8192, 8192, bn=128, iters=3)
+    bench(8192, 8192, 8192, bn=1256, iters=3)
+    if len(sys.argv) > 1 and sys.argv[1] == 'enc':
+        sys.exit(0)
     print('--- decode-step shapes (swap-AB)')
     for fl in (True, False):
         bench(64, 2304, 768, out_bf16=0, transposed=1, flush_l2=fl)
