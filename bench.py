@@ -157,6 +157,8 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true')
+    ap.add_argument('--pipeline', type=int, default=2, choices=[1, 2],
+                    help='batches in flight (2: the encoder of batch i+1 overlaps the decode loop of batch i)')
     ap.add_argument('--ncu-range', action='store_true',
                     help='bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)')
     args = ap.parse_args()
@@ -197,66 +199,109 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_step_device():
-        out = model({'image': img_dev})
+    def finish_device(pend):
+        out = pend.result()
         toks, lps = out['predictions'], out['logprobs']
         if world > 1:
             toks, lps = gather_captions(toks, lps, n_total)
         return toks
 
+    def run_device(k, depth):
+        """k steps; depth 1 = one batch at a time (model(batch)), depth 2 = the next batch is submitted before the
+        previous result is collected, so its encoder overlaps the previous batch's latency-bound decode loop."""
+        pend, toks = None, None
+        for _ in range(k):
+            h = model.submit({'image': img_dev}, slot=None if depth > 1 else 0)
+            if pend is not None:
+                toks = finish_device(pend)
+            pend = h
+            if depth == 1:
+                toks = finish_device(pend)
+                pend = None
+        if pend is not None:
+            toks = finish_device(pend)
+        return toks
+
     # ---------------- device-resident timing (`value`) ----------------
+    results = {}
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            toks = one_step_device()
-        barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        launches0 = model.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if args.ncu_range:
-            torch.cuda.profiler.start()
-        e0.record(stream)
-        for _ in range(args.steps):
-            toks = one_step_device()
-        e1.record(stream)
-        barrier()
-        if args.ncu_range:
-            torch.cuda.profiler.stop()
-        ms = e0.elapsed_time(e1)
-        launches = model.launch_count() - launches0
-        assert toks.shape[0] == n_total and toks.shape[1] == MAX_STEPS
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+        for depth in (1, args.pipeline):
+            if depth in results:
+                continue
+            toks = run_device(args.warmup, depth)
+            barrier()
+            if depth == args.pipeline:
+                sampler = ClockSampler(local)
+                if rank == 0:
+                    sampler.start()
+            launches0 = model.launch_count()
+            if args.ncu_range and depth == args.pipeline:
+                torch.cuda.profiler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            toks = run_device(args.steps, depth)
+            torch.cuda.current_stream().wait_stream(stream)
+            for sl in model._slots:          # the pipelined engines run on their own streams: join them before e1
+                if sl['stream'] is not None:
+                    stream.wait_stream(sl['stream'])
+            e1.record(stream)
+            barrier()
+            if args.ncu_range and depth == args.pipeline:
+                torch.cuda.profiler.stop()
+            ms_d = e0.elapsed_time(e1)
+            t = torch.tensor([ms_d], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            results[depth] = (t.item(), model.launch_count() - launches0)
+            assert toks.shape[0] == n_total and toks.shape[1] == MAX_STEPS
+    ms, launches = results[args.pipeline]
     value = n_total * args.steps / (ms / 1e3)
+    sync_value = n_total * args.steps / (results[1][0] / 1e3)
 
     # ---------------- end to end through the C ABI with HOST buffers (`e2e`) ----------------
-    lib, _ = model._ensure_engine()
     sp = model._search_struct()
-    tok_host = torch.empty((B, MAX_STEPS), dtype=torch.long).pin_memory()
-    lp_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    n_e2e_slots = args.pipeline
+    slots = []
+    for k in range(n_e2e_slots):
+        lib, _ = model._ensure_engine(k)
+        slots.append(dict(engine=model._slots[k]['engine'],
+                          stream=stream if k == 0 else torch.cuda.Stream(device=dev),
+                          tok=torch.empty((B, MAX_STEPS), dtype=torch.long).pin_memory(),
+                          lp=torch.empty((B,), dtype=torch.float32).pin_memory(), busy=False))
     n_out = ctypes.c_int32(0)
 
-    def one_step_host():
-        _lib.check(lib.gitb200_generate_host(model._engine, img_host.data_ptr(), B, 0, None, 0, ctypes.byref(sp),
-                                             tok_host.data_ptr(), lp_host.data_ptr(), ctypes.byref(n_out),
-                                             stream.cuda_stream), model._engine, 'generate_host')
+    def e2e_finish(sl):
+        _lib.check(lib.gitb200_generate_finish(sl['engine'], ctypes.byref(n_out)), sl['engine'], 'generate_finish')
+        sl['busy'] = False
         if world > 1:
-            gather_captions(tok_host.to(dev, non_blocking=True), lp_host.to(dev, non_blocking=True), n_total)
+            gather_captions(sl['tok'].to(dev, non_blocking=True), sl['lp'].to(dev, non_blocking=True), n_total)
+
+    def run_host(k):
+        """k steps through the C ABI with HOST buffers: H2D pixels, generate, D2H tokens; `pipeline` engines in flight."""
+        for i in range(k):
+            sl = slots[i % n_e2e_slots]
+            if sl['busy']:
+                e2e_finish(sl)
+            _lib.check(lib.gitb200_generate_host_async(sl['engine'], img_host.data_ptr(), B, 0, None, 0, ctypes.byref(sp),
+                                                       sl['tok'].data_ptr(), sl['lp'].data_ptr(), sl['stream'].cuda_stream),
+                       sl['engine'], 'generate_host_async')
+            sl['busy'] = True
+        for sl in slots:
+            if sl['busy']:
+                e2e_finish(sl)
 
     with torch.cuda.stream(stream):
-        for _ in range(2):
-            one_step_host()
+        run_host(2 * n_e2e_slots)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
-            one_step_host()
+        run_host(args.steps)
+        for sl in slots[1:]:
+            stream.wait_stream(sl['stream'])
         e1.record(stream)
         barrier()
         ms_e2e = e0.elapsed_time(e1)
+        tok_host, lp_host = slots[0]['tok'], slots[0]['lp']
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,7 +368,11 @@ def main():
                                    'per GPU, random-init weights' % B,
                        'global_batch': n_total, 'per_gpu_batch': B, 'parallelism': 'image-parallel x%d + 1 all_gather' % world,
                        'l2': 'inputs larger than L2: each step streams ~0.3 GB weights + 0.23 GB image K/V + activations (> 126 MB)',
-                       'compute': 'bf16 operands, fp32 accumulate, fp32 residual stream'},
+                       'compute': 'bf16 operands, fp32 accumulate, fp32 residual stream',
+                       'pipeline': '%d batches in flight (two engines on two streams: encoder + prefill of batch i+1 overlap the '
+                                   'latency-bound decode loop of batch i; every step does all of its work inside the timed region)' % args.pipeline
+                       if args.pipeline > 1 else '1 (synchronous model(batch) calls)'},
+            'sync_value': sync_value,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': img_host.numel() * 4, 'd2h_bytes_per_step': tok_host.numel() * 8 + lp_host.numel() * 4},
             'gpu_launches': int(launches),

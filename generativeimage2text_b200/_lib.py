@@ -40,6 +40,11 @@ SIGNATURES = {
                                  c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int32), c_void_p, c_void_p]),
     'gitb200_generate_host': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.POINTER(Search),
                                       c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int32), c_void_p]),
+    'gitb200_generate_async': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.POINTER(Search), c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    'gitb200_generate_host_async': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.POINTER(Search),
+                                            c_void_p, c_void_p, c_void_p]),
+    'gitb200_generate_finish': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_int32)]),
     'gitb200_launch_count': (c_int64, [c_void_p]),
     'gitb200_set_option': (c_int, [c_void_p, c_char_p, c_int64]),
     'gitb200_debug_timeline': (c_int, [c_int, c_void_p, c_int]),

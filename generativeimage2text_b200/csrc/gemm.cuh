@@ -43,7 +43,7 @@ struct GemmParams {
 
 // Epilogue variants are compile-time (the runtime-flag version spent ~700 warp instructions per 32x32 chunk,
 // which made every K=768 GEMM of the encoder epilogue-issue bound).
-constexpr int EPI_TRANSPOSED = 1, EPI_BF16 = 2, EPI_RESID = 4, EPI_ATOMIC = 8, EPI_ACT_SHIFT = 4;
+constexpr int EPI_TRANSPOSED = 1, EPI_BF16 = 2, EPI_RESID = 4, EPI_ATOMIC = 8, EPI_ACT_SHIFT = 4, EPI_DIRECT = 64;
 constexpr int epi_code(bool transposed, bool bf16, bool resid, bool atomic, int act) {
   return (transposed ? EPI_TRANSPOSED : 0) | (bf16 ? EPI_BF16 : 0) | (resid ? EPI_RESID : 0) | (atomic ? EPI_ATOMIC : 0) |
          (act << EPI_ACT_SHIFT);
@@ -85,7 +85,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr bool kBf16 = (EPI & EPI_BF16) != 0;
   constexpr bool kResid = (EPI & EPI_RESID) != 0;
   constexpr bool kAtomic = (EPI & EPI_ATOMIC) != 0;
-  constexpr int kAct = EPI >> EPI_ACT_SHIFT;
+  constexpr int kAct = (EPI >> EPI_ACT_SHIFT) & 3;
+  constexpr bool kDirect = (EPI & EPI_DIRECT) != 0;   // thread = row, registers -> global (no smem transpose)
   if (p.pdl) griddep_launch();
   if (p.pdl) tl_mark(100000 + 1000 + static_cast<int>(gridDim.x));
   // `skip` (decode finished) only changes between steps, which are separated by full dependencies
@@ -250,7 +251,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ---- per-tile row bookkeeping (normal mode): output row offsets of this lane's 8 rows ----
       long long ooff[8];
       uint32_t okmask = 0;
-      if (!kTransposed) {
+      long long drow_off = 0;   // direct epilogue: output row offset of this thread's row (row0 + lane)
+      bool drow_ok = false;
+      if (!kTransposed && kDirect) {
+        const int row = row0 + lane;
+        const int bq = row / p.rows_per_batch;
+        drow_off = (static_cast<long long>(bq) * p.batch_stride + (row - bq * p.rows_per_batch) + p.row_offset) * p.ldo;
+        drow_ok = row < p.M && store_ok;
+      } else if (!kTransposed) {
         int bq = (row0 + rsub) / p.rows_per_batch;
         int sq = (row0 + rsub) - bq * p.rows_per_batch;
 #pragma unroll
@@ -272,7 +280,49 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN + c * 32, r);
         tmem_ld_wait();
-        if (!kTransposed) {
+        if (!kTransposed && kDirect) {
+          // thread = row: 32 consecutive outputs of one row straight from registers (64 B bf16 / 128 B fp32 per lane).
+          // Fewer instructions than the staged transpose (no STS/LDS/syncwarp), paid with 32 L1 wavefronts per store.
+          int seg = 0;
+          if (!single_seg) seg = n0 / p.seg_n;
+          const int nn = n0 - seg * p.seg_n;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
+          if (kAct != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_ct<kAct>(v[j]);
+          }
+          if (drow_ok) {
+            if (kResid) {
+              const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row0 + lane) * p.ld_resid + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r4 = rp[j];
+                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+              }
+            }
+            if (kBf16) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + drow_off + nn);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            } else {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + drow_off + nn);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        } else if (!kTransposed) {
           // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
 #pragma unroll
           for (int j = 0; j < 8; ++j)

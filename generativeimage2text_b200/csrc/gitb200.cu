@@ -102,6 +102,8 @@ struct gitb200_engine {
   // decode GEMMs through skinny.cuh (mma.sync, fewer dependent hops per CTA) instead of swap-AB tcgen05. Measured on
   // B200 (bench.py, 10 steps): 18.89 ms/step lean vs 18.09 ms tcgen05 -> off by default, kept for comparison.
   bool use_lean = false;
+  bool epi_direct = false; // measured: the staged transpose is faster on every ViT shape (direct stores are LSU bound)
+  // (kept switchable)   // normal-mode GEMM epilogue: registers -> global (true) or staged smem transpose (false)
   bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
 
   // derived geometry
@@ -138,6 +140,13 @@ struct gitb200_engine {
   int last_gemm_grid = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t own_event = nullptr;
+  // asynchronous generate: enqueue now, read the loop state back in gitb200_generate_finish
+  StepState* host_state = nullptr;   // pinned [kMaxLanes]
+  bool pending = false;
+  int pend_lanes = 1, pend_max_steps = 0;
+  bool pend_beam = false;
+  cudaStream_t pend_stream = nullptr;
+  int64_t* pend_tok_host = nullptr;  // host-buffer variant: results land here
   // decode lanes: the greedy batch is split into independent row groups whose (latency-bound) kernel chains run
   // concurrently on separate streams -- forked and joined inside the captured step graph
   int lanes_opt = 1;   // measured: the chains are latency bound, concurrent lanes do not shorten a step (kept as an option)
@@ -300,13 +309,18 @@ static int launch_gemm2_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t 
 template <int BN>
 static int launch_gemm2_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
   const GemmParams& p = c.p;
-  const int code = epi_code(false, p.out_bf16 != 0, p.resid != nullptr, false, p.act);
+  const int code = epi_code(false, p.out_bf16 != 0, p.resid != nullptr, false, p.act) | (h->epi_direct ? EPI_DIRECT : 0);
   switch (code) {
     case epi_code(false, true, false, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
     case epi_code(false, false, true, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, false, true, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
     case epi_code(false, false, false, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, false, false, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
     case epi_code(false, true, false, false, ACT_QUICKGELU): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT>(h, c, st);
     case epi_code(false, true, false, false, ACT_GELU_ERF): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT>(h, c, st);
     default: break;
   }
   return fail(h, "gemm2: epilogue combination not instantiated");
@@ -316,14 +330,20 @@ static int launch_gemm2_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st
 template <int BN>
 static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
   const GemmParams& p = c.p;
-  const int code = epi_code(p.transposed != 0, p.out_bf16 != 0, p.resid != nullptr, p.atomic != 0, p.act);
+  const int code = epi_code(p.transposed != 0, p.out_bf16 != 0, p.resid != nullptr, p.atomic != 0, p.act) |
+                   ((h->epi_direct && !p.transposed) ? EPI_DIRECT : 0);
   if constexpr (BN == 192 || BN == 256 || BN == 128) {
     switch (code) {
       case epi_code(false, true, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
       case epi_code(false, false, true, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, false, true, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
       case epi_code(false, false, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, false, false, false, ACT_NONE)>(h, c, st);
+      case epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
       case epi_code(false, true, false, false, ACT_QUICKGELU): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT>(h, c, st);
       case epi_code(false, true, false, false, ACT_GELU_ERF): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF)>(h, c, st);
+      case epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT>(h, c, st);
       default: break;
     }
   }
@@ -534,6 +554,7 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
   if (strcmp(name, "use_lean") == 0) { h->use_lean = value != 0; return 0; }
   if (strcmp(name, "use_2cta") == 0) { h->use_2cta = value != 0; return 0; }
+  if (strcmp(name, "epi_direct") == 0) { h->epi_direct = value != 0; return 0; }
   if (strcmp(name, "lanes") == 0) { h->lanes_opt = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : static_cast<int>(value)); return 0; }
   return fail(h, "unknown option %s", name);
 }
@@ -599,6 +620,7 @@ extern "C" void gitb200_destroy(gitb200_engine* h) {
   if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
   for (int i = 0; i < kMaxLanes; ++i) { if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->host_state) cudaFreeHost(h->host_state);
   if (h->own_event) cudaEventDestroy(h->own_event);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   release_all(h);

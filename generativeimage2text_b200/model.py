@@ -58,6 +58,21 @@ class GeneratorWithBeamSearch(object):
             raise NotImplementedError('repetition_penalty / temperature are not used by get_git_model')
 
 
+class _Pending(object):
+    """Handle of an enqueued `model(batch)` (see GitB200CaptioningModel.submit)."""
+
+    def __init__(self, model, slot, sp, P, tokens, logprobs, step_logits, keep):
+        self.model, self.slot, self.sp, self.P = model, slot, sp, P
+        self.tokens, self.logprobs, self.step_logits, self._keep = tokens, logprobs, step_logits, keep
+        self._out = None
+
+    def result(self):
+        if self._out is None:
+            self._out = self.model._finish(self)
+            self._keep = None
+        return self._out
+
+
 class _Holder(nn.Module):
     """Attribute container so that parameters get the reference's dotted names."""
 
@@ -116,9 +131,12 @@ class GitB200CaptioningModel(nn.Module):
             image_size=self.image_size, patch=enc['patch'], enc_width=enc['width'], enc_layers=enc['layers'],
             enc_heads=enc['heads'], dec_hidden=HIDDEN, dec_layers=DEC_LAYERS, dec_heads=DEC_HEADS, dec_ffn=FFN,
             vocab=VOCAB, max_positions=MAX_POS, num_frames_emb=n_emb, sos_id=self.sos_index, eos_id=self.eos_index)
-        self._engine = None
+        # engine slots: slot 0 serves `model(batch)`; `submit()` round-robins over `n_slots` engines, each on its own
+        # stream, so the encoder of one batch overlaps the latency-bound decode loop of the previous one
+        self.n_slots = 2
+        self._slots = [dict(engine=None, sig=None, stream=None, pending=None) for _ in range(self.n_slots)]
         self._engine_device = None
-        self._weights_sig = None
+        self._next_slot = 0
 
     # ---------------------------------------------------------------- engine plumbing
     def _device(self):
@@ -127,40 +145,49 @@ class GitB200CaptioningModel(nn.Module):
     def _weights_signature(self):
         return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
 
-    def _ensure_engine(self):
+    @property
+    def _engine(self):
+        return self._slots[0]['engine']
+
+    def _ensure_engine(self, slot=0):
         dev = self._device()
         if dev.type != 'cuda':
             raise RuntimeError('the gitb200 engine runs on CUDA devices only (sm_100a); call model.cuda() first. '
                                'There is no CPU path.')
         lib = _lib.load()
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        if self._engine is None or self._engine_device != dev:
+        if self._engine_device is not None and self._engine_device != dev:
             self.release()
+        self._engine_device = dev
+        sl = self._slots[slot]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if sl['engine'] is None:
             h = ctypes.c_void_p()
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
-            self._engine, self._engine_device, self._weights_sig = h, dev, None
+            sl['engine'], sl['sig'] = h, None
             import os
-            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'lanes'):   # debugging switches, e.g. GITB200_LANES=1
-                v = os.environ.get('GITB200_' + opt.upper())
+            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'epi_direct', 'lanes'):
+                v = os.environ.get('GITB200_' + opt.upper())      # debugging switches, e.g. GITB200_USE_2CTA=0
                 if v is not None:
                     _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')
         sig = self._weights_signature()
-        if sig != self._weights_sig:
+        if sig != sl['sig']:
+            eng = sl['engine']
             for key, p in self.state_dict(keep_vars=True).items():
                 t = p.detach()
                 if t.dtype != torch.float32 or not t.is_contiguous():
                     t = t.float().contiguous()
                 shape = (ctypes.c_int64 * t.dim())(*t.shape)
-                _lib.check(lib.gitb200_set_weight(self._engine, key.encode(), t.data_ptr(), shape, t.dim(), _lib.F32,
-                                                  stream), self._engine, 'set_weight(%s)' % key)
-            _lib.check(lib.gitb200_finalize_weights(self._engine, stream), self._engine, 'finalize_weights')
-            self._weights_sig = sig
+                _lib.check(lib.gitb200_set_weight(eng, key.encode(), t.data_ptr(), shape, t.dim(), _lib.F32,
+                                                  stream), eng, 'set_weight(%s)' % key)
+            _lib.check(lib.gitb200_finalize_weights(eng, stream), eng, 'finalize_weights')
+            sl['sig'] = sig
         return lib, stream
 
     def release(self):
-        if self._engine is not None:
-            _lib.load().gitb200_destroy(self._engine)
-            self._engine = None
+        for sl in self._slots:
+            if sl['engine'] is not None:
+                _lib.load().gitb200_destroy(sl['engine'])
+                sl['engine'], sl['sig'], sl['pending'] = None, None, None
 
     def __del__(self):
         try:
@@ -170,11 +197,14 @@ class GitB200CaptioningModel(nn.Module):
 
     def set_engine_option(self, name, value):
         """Engine switches: 'use_graph', 'use_pdl', 'use_chain' (0/1), 'lanes' (1..4 concurrent decode row groups)."""
-        lib, _ = self._ensure_engine()
-        _lib.check(lib.gitb200_set_option(self._engine, name.encode(), int(value)), self._engine, 'set_option')
+        for k in range(self.n_slots):
+            if k == 0 or self._slots[k]['engine'] is not None:
+                lib, _ = self._ensure_engine(k)
+                _lib.check(lib.gitb200_set_option(self._slots[k]['engine'], name.encode(), int(value)), self._slots[k]['engine'], 'set_option')
 
     def launch_count(self):
-        return int(_lib.load().gitb200_launch_count(self._engine)) if self._engine is not None else 0
+        lib = _lib.load()
+        return sum(int(lib.gitb200_launch_count(sl['engine'])) for sl in self._slots if sl['engine'] is not None)
 
     def _search_struct(self):
         d = self.decoder
@@ -213,14 +243,35 @@ class GitB200CaptioningModel(nn.Module):
         batch: {'image': FloatTensor[B,3,H,W] | [FloatTensor[B,3,H,W]] * frames, 'prefix'?: LongTensor[1,P]}
         forced_tokens / return_step_logits are parity-test hooks (teacher forcing, raw per-step logits).
         """
+        return self.submit(batch, forced_tokens, return_step_logits, slot=0).result()
+
+    @torch.no_grad()
+    def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None):
+        """Enqueue `model(batch)` without waiting: returns a handle whose `.result()` gives the reference's output
+        dict.  Successive submits alternate between two engines / streams (pipeline depth 2)."""
         if self.training:
             raise NotImplementedError('training (loss / SCST branches) is out of scope: call model.eval()')
         if 'image' not in batch:
             raise NotImplementedError("batch without 'image' is not supported")
         if 'context' in batch:
             raise NotImplementedError("'context' batches are not produced by the reference inference path")
-        lib, stream = self._ensure_engine()
+        if slot is None:
+            slot = self._next_slot
+            self._next_slot = (self._next_slot + 1) % self.n_slots
+        sl = self._slots[slot]
+        if sl['pending'] is not None:
+            sl['pending'].result()
+        lib, _ = self._ensure_engine(slot)
+        eng = sl['engine']
         dev = self._device()
+        cur = torch.cuda.current_stream(dev)
+        if slot == 0:
+            stream = cur                      # synchronous path: the caller's stream (stream 0 -> engine-owned stream)
+        else:
+            if sl['stream'] is None:
+                sl['stream'] = torch.cuda.Stream(device=dev)
+            stream = sl['stream']
+            stream.wait_stream(cur)           # inputs produced on the caller's stream
         x, B, frames = self._pack_images(batch['image'])
         sp = self._search_struct()
         prefix, P = None, 0
@@ -231,9 +282,7 @@ class GitB200CaptioningModel(nn.Module):
             prefix = batch['prefix'].to(device=dev, dtype=torch.long).contiguous().view(-1)
             P = prefix.numel()
         tokens = torch.empty((B, sp.max_steps), dtype=torch.long, device=dev)
-        n_lp = B
-        logprobs = torch.empty((n_lp,), dtype=torch.float32, device=dev)
-        out_len = ctypes.c_int32(0)
+        logprobs = torch.empty((B,), dtype=torch.float32, device=dev)
         forced = None
         if forced_tokens is not None:
             forced = forced_tokens.to(device=dev, dtype=torch.long).contiguous()
@@ -242,11 +291,25 @@ class GitB200CaptioningModel(nn.Module):
         if return_step_logits:
             rows = B * (sp.beam_size if sp.mode == _lib.SEARCH_BEAM else 1)
             step_logits = torch.zeros((sp.max_steps - max(P, 1), rows, VOCAB), dtype=torch.float32, device=dev)
-        _lib.check(lib.gitb200_generate(
-            self._engine, x.data_ptr(), B, frames, prefix.data_ptr() if prefix is not None else None, P,
+        for t in (x, prefix, forced):
+            if t is not None and stream is not cur:
+                t.record_stream(stream)
+        _lib.check(lib.gitb200_generate_async(
+            eng, x.data_ptr(), B, frames, prefix.data_ptr() if prefix is not None else None, P,
             ctypes.byref(sp), forced.data_ptr() if forced is not None else None, tokens.data_ptr(),
-            logprobs.data_ptr(), ctypes.byref(out_len), step_logits.data_ptr() if step_logits is not None else None,
-            stream), self._engine, 'generate')
+            logprobs.data_ptr(), step_logits.data_ptr() if step_logits is not None else None,
+            stream.cuda_stream), eng, 'generate')
+        pend = _Pending(self, slot, sp, P, tokens, logprobs, step_logits, (x, prefix, forced))
+        sl['pending'] = pend
+        return pend
+
+    def _finish(self, pend):
+        lib = _lib.load()
+        sl = self._slots[pend.slot]
+        out_len = ctypes.c_int32(0)
+        _lib.check(lib.gitb200_generate_finish(sl['engine'], ctypes.byref(out_len)), sl['engine'], 'generate_finish')
+        sl['pending'] = None
+        sp, P, tokens, logprobs = pend.sp, pend.P, pend.tokens, pend.logprobs
         n = out_len.value
         if sp.mode == _lib.SEARCH_GREEDY:
             if n < 0:   # every first token was EOS (reference layers/decoder.py:279-291)
@@ -263,8 +326,8 @@ class GitB200CaptioningModel(nn.Module):
             pred = tokens[:, P:] if P else tokens
             lp = logprobs[:, None]
         out = {'predictions': pred, 'logprobs': lp}
-        if return_step_logits:
-            out['step_logits'] = step_logits
+        if pend.step_logits is not None:
+            out['step_logits'] = pend.step_logits
         return out
 
     # ---------------------------------------------------------------- parity hooks (intermediate activations)

@@ -116,6 +116,18 @@ int gitb200_generate_host(gitb200_engine* h, const float* images_host, int batch
                           const int64_t* prefix_host, int prefix_len, const gitb200_search* search,
                           int64_t* tokens_out_host, float* logprobs_out_host, int32_t* out_len_host, void* stream);
 
+/* Asynchronous form of the two calls above (same arguments minus out_len_host): everything is enqueued on `stream`
+ * and the call returns; gitb200_generate_finish synchronises that stream and reports the loop length.  One call may
+ * be in flight per engine; a host that keeps two engines (two streams) busy overlaps the encoder of batch i+1 with
+ * the latency-bound decode loop of batch i (bench.py "pipeline": 2). Output buffers must stay valid until finish. */
+int gitb200_generate_async(gitb200_engine* h, const float* images_dev, int batch, int frames, const int64_t* prefix_dev,
+                           int prefix_len, const gitb200_search* search, const int64_t* forced_dev,
+                           int64_t* tokens_out_dev, float* logprobs_out_dev, float* step_logits_dev, void* stream);
+int gitb200_generate_host_async(gitb200_engine* h, const float* images_host, int batch, int frames,
+                                const int64_t* prefix_host, int prefix_len, const gitb200_search* search,
+                                int64_t* tokens_out_host, float* logprobs_out_host, void* stream);
+int gitb200_generate_finish(gitb200_engine* h, int32_t* out_len_host);
+
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t gitb200_launch_count(const gitb200_engine* h);
 /* Enable/disable CUDA-graph replay of the decode step (default on). */
