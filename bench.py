@@ -149,6 +149,8 @@ def run_reference_arm(args, rank, world):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('GITB200_BENCH_WATCHDOG_S', '240')), exit=True)   # a hung run reports where
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -157,7 +159,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true')
-    ap.add_argument('--pipeline', type=int, default=2, choices=[1, 2],
+    ap.add_argument('--pipeline', type=int, default=4, choices=[1, 2, 3, 4],
                     help='batches in flight (2: the encoder of batch i+1 overlaps the decode loop of batch i)')
     ap.add_argument('--ncu-range', action='store_true',
                     help='bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)')
@@ -209,17 +211,14 @@ def main():
     def run_device(k, depth):
         """k steps; depth 1 = one batch at a time (model(batch)), depth 2 = the next batch is submitted before the
         previous result is collected, so its encoder overlaps the previous batch's latency-bound decode loop."""
-        pend, toks = None, None
+        pend, toks = [], None
         for _ in range(k):
-            h = model.submit({'image': img_dev}, slot=None if depth > 1 else 0)
-            if pend is not None:
-                toks = finish_device(pend)
-            pend = h
-            if depth == 1:
-                toks = finish_device(pend)
-                pend = None
-        if pend is not None:
-            toks = finish_device(pend)
+            h = model.submit({'image': img_dev}, slot=None if depth > 1 else 0, depth=depth)
+            pend.append(h)
+            if len(pend) >= depth:
+                toks = finish_device(pend.pop(0))
+        while pend:
+            toks = finish_device(pend.pop(0))
         return toks
 
     # ---------------- device-resident timing (`value`) ----------------
@@ -228,7 +227,7 @@ def main():
         for depth in (1, args.pipeline):
             if depth in results:
                 continue
-            toks = run_device(args.warmup, depth)
+            toks = run_device(max(args.warmup, 2 * depth), depth)   # every engine slot past its first (capturing) call
             barrier()
             if depth == args.pipeline:
                 sampler = ClockSampler(local)
@@ -369,8 +368,9 @@ def main():
                        'global_batch': n_total, 'per_gpu_batch': B, 'parallelism': 'image-parallel x%d + 1 all_gather' % world,
                        'l2': 'inputs larger than L2: each step streams ~0.3 GB weights + 0.23 GB image K/V + activations (> 126 MB)',
                        'compute': 'bf16 operands, fp32 accumulate, fp32 residual stream',
-                       'pipeline': '%d batches in flight (two engines on two streams: encoder + prefill of batch i+1 overlap the '
-                                   'latency-bound decode loop of batch i; every step does all of its work inside the timed region)' % args.pipeline
+                       'pipeline': '%d batches of 64 in flight (one engine + stream each: encoder / prefill of later batches overlap the '
+                                   'latency-bound decode loops of earlier ones; every step does all of its work inside the timed '
+                                   'region; sync_value = one batch at a time through model(batch))' % args.pipeline
                        if args.pipeline > 1 else '1 (synchronous model(batch) calls)'},
             'sync_value': sync_value,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,

@@ -102,6 +102,9 @@ struct gitb200_engine {
   // decode GEMMs through skinny.cuh (mma.sync, fewer dependent hops per CTA) instead of swap-AB tcgen05. Measured on
   // B200 (bench.py, 10 steps): 18.89 ms/step lean vs 18.09 ms tcgen05 -> off by default, kept for comparison.
   bool use_lean = false;
+  int decode_ctas = 0;    // cap on CTAs per decode-step kernel (0 = none): smaller footprints let the chains of several
+                          // batches in flight overlap instead of serialising on the 148-CTA LM head / 296-CTA attention
+  int sm_reserve = 0;     // SMs the persistent encoder / prefill GEMMs leave free (for decode chains of other batches in flight)
   bool epi_direct = false; // measured: the staged transpose is faster on every ViT shape (direct stores are LSU bound)
   // (kept switchable)   // normal-mode GEMM epilogue: registers -> global (true) or staged smem transpose (false)
   bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
@@ -279,7 +282,9 @@ static int launch_gemm_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t s
   const int m_tiles = (c.p.M + 127) / 128;
   const int n_tiles = (c.p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles * c.p.k_splits;
-  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+  int sms = (c.p.transposed || c.p.M < 2048) ? h->num_sms : h->num_sms - h->sm_reserve;
+  if (c.p.transposed && h->decode_ctas > 0 && h->decode_ctas < sms) sms = h->decode_ctas;
+  const int grid = tiles < sms ? tiles : sms;
   h->last_gemm_grid = grid;
   CK(launch_k(c.p.pdl != 0, gemm_bf16_tcgen05<BN, EPI>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
   CKL(h, "gemm_bf16_tcgen05");
@@ -300,7 +305,7 @@ static int launch_gemm2_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t 
   const int m_tiles = (c.p.M + 255) / 256;
   const int n_tiles = (c.p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
-  const int pairs = std::min(tiles, h->num_sms / 2);
+  const int pairs = std::min(tiles, (h->num_sms - h->sm_reserve) / 2);
   h->last_gemm_grid = 2 * pairs;
   CK(launch_k(false, gemm2_bf16_tcgen05<BN, EPI>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
   CKL(h, "gemm2_bf16_tcgen05");
@@ -553,6 +558,8 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
   if (strcmp(name, "use_lean") == 0) { h->use_lean = value != 0; return 0; }
+  if (strcmp(name, "decode_ctas") == 0) { h->decode_ctas = value < 0 ? 0 : static_cast<int>(value); return 0; }
+  if (strcmp(name, "sm_reserve") == 0) { h->sm_reserve = value < 0 ? 0 : (value > 64 ? 64 : static_cast<int>(value)); return 0; }
   if (strcmp(name, "use_2cta") == 0) { h->use_2cta = value != 0; return 0; }
   if (strcmp(name, "epi_direct") == 0) { h->epi_direct = value != 0; return 0; }
   if (strcmp(name, "lanes") == 0) { h->lanes_opt = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : static_cast<int>(value)); return 0; }
@@ -1016,7 +1023,7 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
     CUtensorMap tk, tv;
     TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
     TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
-    dim3 grid(std::min(h->attn_grid, ln_.nb * h->cfg.dec_heads));
+    dim3 grid(std::min(h->decode_ctas > 0 ? std::min(h->attn_grid, h->decode_ctas) : h->attn_grid, ln_.nb * h->cfg.dec_heads));
     if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);

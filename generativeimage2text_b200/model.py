@@ -133,7 +133,7 @@ class GitB200CaptioningModel(nn.Module):
             vocab=VOCAB, max_positions=MAX_POS, num_frames_emb=n_emb, sos_id=self.sos_index, eos_id=self.eos_index)
         # engine slots: slot 0 serves `model(batch)`; `submit()` round-robins over `n_slots` engines, each on its own
         # stream, so the encoder of one batch overlaps the latency-bound decode loop of the previous one
-        self.n_slots = 2
+        self.n_slots = 4
         self._slots = [dict(engine=None, sig=None, stream=None, pending=None) for _ in range(self.n_slots)]
         self._engine_device = None
         self._next_slot = 0
@@ -165,7 +165,7 @@ class GitB200CaptioningModel(nn.Module):
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
             sl['engine'], sl['sig'] = h, None
             import os
-            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'epi_direct', 'lanes'):
+            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'epi_direct', 'lanes', 'sm_reserve', 'decode_ctas'):
                 v = os.environ.get('GITB200_' + opt.upper())      # debugging switches, e.g. GITB200_USE_2CTA=0
                 if v is not None:
                     _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')
@@ -246,9 +246,9 @@ class GitB200CaptioningModel(nn.Module):
         return self.submit(batch, forced_tokens, return_step_logits, slot=0).result()
 
     @torch.no_grad()
-    def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None):
+    def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None, depth=2):
         """Enqueue `model(batch)` without waiting: returns a handle whose `.result()` gives the reference's output
-        dict.  Successive submits alternate between two engines / streams (pipeline depth 2)."""
+        dict.  Successive submits rotate over `depth` engines / streams (each engine: one call in flight)."""
         if self.training:
             raise NotImplementedError('training (loss / SCST branches) is out of scope: call model.eval()')
         if 'image' not in batch:
@@ -256,8 +256,9 @@ class GitB200CaptioningModel(nn.Module):
         if 'context' in batch:
             raise NotImplementedError("'context' batches are not produced by the reference inference path")
         if slot is None:
-            slot = self._next_slot
-            self._next_slot = (self._next_slot + 1) % self.n_slots
+            depth = max(1, min(int(depth), self.n_slots))
+            slot = self._next_slot % depth
+            self._next_slot = (slot + 1) % depth
         sl = self._slots[slot]
         if sl['pending'] is not None:
             sl['pending'].result()
