@@ -159,7 +159,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true')
-    ap.add_argument('--pipeline', type=int, default=4, choices=[1, 2, 3, 4],
+    ap.add_argument('--pipeline', type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help='batches in flight (2: the encoder of batch i+1 overlaps the decode loop of batch i)')
     ap.add_argument('--ncu-range', action='store_true',
                     help='bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)')
@@ -186,6 +186,7 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     B = args.batch
+    os.environ.setdefault('GITB200_SLOTS', str(max(4, args.pipeline)))
     model = get_git_model(Tok(), {})
     model.load_state_dict(synthetic_state_dict({}, 0, 'init'), strict=True)
     model = model.to(dev).eval()

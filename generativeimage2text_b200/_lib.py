@@ -5,7 +5,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libgitb200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_int64, c_float, c_char_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_char_p
 c_ll = ctypes.c_longlong
@@ -33,6 +33,7 @@ SIGNATURES = {
     'gitb200_abi_version': (c_int, []),
     'gitb200_set_weight': (c_int, [c_void_p, c_char_p, c_void_p, ctypes.POINTER(c_int64), c_int, c_int, c_void_p]),
     'gitb200_finalize_weights': (c_int, [c_void_p, c_void_p]),
+    'gitb200_share_weights': (c_int, [c_void_p, c_void_p]),
     'gitb200_encode': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'gitb200_prefill': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'gitb200_decode_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

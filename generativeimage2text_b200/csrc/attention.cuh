@@ -252,7 +252,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int n_my = (n_items - static_cast<int>(blockIdx.x) + G - 1) / G;
   const int n_units = n_my * n_chunks;
 
-  griddep_launch();
+  griddep_launch_early();
   tl_mark(100003);
   if (tid == 0) {
     tma_prefetch_desc(&tmK);
@@ -290,6 +290,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     griddep_wait();
     finished = (p.state != nullptr && p.state->finished);
   }
+  griddep_launch_late();
   if (finished) {  // never leave with a bulk copy in flight into this CTA's shared memory
     mbar_wait(&bars[0], 0);
     if (n_units > 1) mbar_wait(&bars[1], 0);

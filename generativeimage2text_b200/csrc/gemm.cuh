@@ -87,7 +87,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr bool kAtomic = (EPI & EPI_ATOMIC) != 0;
   constexpr int kAct = (EPI >> EPI_ACT_SHIFT) & 3;
   constexpr bool kDirect = (EPI & EPI_DIRECT) != 0;   // thread = row, registers -> global (no smem transpose)
-  if (p.pdl) griddep_launch();
+  if (p.pdl) griddep_launch_early();
   if (p.pdl) tl_mark(100000 + 1000 + static_cast<int>(gridDim.x));
   // `skip` (decode finished) only changes between steps, which are separated by full dependencies
   if ((!p.pdl || p.chain.counters != nullptr) && p.skip != nullptr && *p.skip != 0) return;  // uniform over the grid
@@ -158,6 +158,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (chained) chain_wait(p.chain);
   else if (p.pdl) griddep_wait();
+  if (p.pdl) griddep_launch_late();
   if (p.pdl) tl_mark(1000 + static_cast<int>(gridDim.x));
 
   if (warp == 0) {

@@ -38,7 +38,7 @@
 using namespace gitb200;
 typedef __nv_bfloat16 bf16;
 
-#define GITB200_ABI_VERSION 1
+#define GITB200_ABI_VERSION 2
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -48,8 +48,10 @@ static thread_local std::string g_create_error;
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;   // false: borrowed from another engine (gitb200_share_weights)
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    if (!owned) return cudaErrorInvalidValue;   // a borrowed buffer is never re-allocated
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -58,9 +60,16 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
+  }
+  void borrow(const DevBuf& o) {
+    release();
+    p = o.p;
+    cap = o.cap;
+    owned = false;
   }
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
@@ -108,6 +117,12 @@ struct gitb200_engine {
   bool epi_direct = false; // measured: the staged transpose is faster on every ViT shape (direct stores are LSU bound)
   // (kept switchable)   // normal-mode GEMM epilogue: registers -> global (true) or staged smem transpose (false)
   bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
+  bool prio_split = false; // decode loop on an engine-owned HIGH-priority stream (encoder / prefill stay on the caller's):
+                          // with several batches in flight the short decode kernels are dispatched ahead of the waves of
+                          // another batch's encoder kernels
+  cudaStream_t prio_stream = nullptr;
+  cudaEvent_t prio_ev[2] = {nullptr, nullptr};
+  const gitb200_engine* weights_from = nullptr;   // non-null: weight buffers are borrowed from that engine
 
   // derived geometry
   int g = 0, L = 0, Kpatch = 0, Kp = 0, d = 0, D = 0, F = 0, V = 0;
@@ -554,6 +569,15 @@ extern "C" int64_t gitb200_launch_count(const gitb200_engine* h) { return h ? h-
 
 extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value) {
   if (!h || !name) return 1;
+  // the captured decode-step graph bakes the launch configuration in: drop it whenever an option changes
+  if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; h->step_graph_key.clear(); }
+  if (strcmp(name, "pdl_late") == 0) {   // process-wide (a __constant__ the chain kernels read)
+    const int v = value != 0 ? 1 : 0;
+    cudaSetDevice(h->device);
+    CK(cudaMemcpyToSymbol(g_pdl_late, &v, sizeof(int)));
+    return 0;
+  }
+  if (strcmp(name, "prio_split") == 0) { h->prio_split = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
@@ -620,6 +644,36 @@ static void release_all(gitb200_engine* h) {
   }
 }
 
+// Weight buffers of an engine, in a fixed order (the same for every engine of one geometry).
+static std::vector<DevBuf*> weight_bufs(gitb200_engine* h) {
+  std::vector<DevBuf*> v = {&h->w_patch, &h->cls, &h->pos_emb, &h->lnpre_g, &h->lnpre_b, &h->lnpost_g, &h->lnpost_b, &h->w_vp,
+                            &h->b_vp, &h->lnvp_g, &h->lnvp_b, &h->words_f32, &h->words_bf16, &h->positions, &h->lnemb_g,
+                            &h->lnemb_b, &h->out_bias, &h->temb};
+  for (auto& l : h->enc)
+    for (DevBuf* b : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.ln2g, &l.ln2b, &l.w1, &l.b1, &l.w2, &l.b2}) v.push_back(b);
+  for (auto& l : h->dec)
+    for (DevBuf* b : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.lnag, &l.lnab, &l.w1, &l.b1, &l.w2, &l.b2, &l.lnog, &l.lnob}) v.push_back(b);
+  return v;
+}
+
+extern "C" int gitb200_share_weights(gitb200_engine* h, gitb200_engine* src) {
+  if (!h || !src) return 1;
+  if (h == src) return fail(h, "share_weights: an engine cannot borrow from itself");
+  if (!src->finalized) return fail(h, "share_weights: the source engine's weights are not finalized");
+  if (src->weights_from != nullptr) return fail(h, "share_weights: the source engine borrows its weights itself");
+  if (h->device != src->device) return fail(h, "share_weights: engines live on different devices");
+  if (memcmp(&h->cfg, &src->cfg, sizeof(gitb200_config)) != 0) return fail(h, "share_weights: geometries differ");
+  if (h->pending) return fail(h, "share_weights: a generate call is in flight");
+  std::vector<DevBuf*> dst = weight_bufs(h), from = weight_bufs(src);
+  for (size_t i = 0; i < dst.size(); ++i) dst[i]->borrow(*from[i]);
+  h->tmaps.clear();
+  if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; h->step_graph_key.clear(); }
+  h->seen = src->seen;
+  h->finalized = true;
+  h->weights_from = src;
+  return 0;
+}
+
 extern "C" void gitb200_destroy(gitb200_engine* h) {
   if (!h) return;
   cudaSetDevice(h->device);
@@ -630,6 +684,8 @@ extern "C" void gitb200_destroy(gitb200_engine* h) {
   if (h->host_state) cudaFreeHost(h->host_state);
   if (h->own_event) cudaEventDestroy(h->own_event);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->prio_stream) cudaStreamDestroy(h->prio_stream);
+  for (int i = 0; i < 2; ++i) if (h->prio_ev[i]) cudaEventDestroy(h->prio_ev[i]);
   release_all(h);
   delete h;
 }
@@ -672,6 +728,7 @@ extern "C" int gitb200_set_weight(gitb200_engine* h, const char* ref_key, const 
   const std::string key(ref_key);
   const int d = h->d, D = h->D, F = h->F, V = h->V, L = h->L;
   auto bad_shape = [&]() { return fail(h, "set_weight(%s): unexpected shape", ref_key); };
+  if (h->weights_from != nullptr) return fail(h, "set_weight(%s): this engine borrows its weights (gitb200_share_weights)", ref_key);
   h->finalized = false;
   int layer = -1;
   char sub[128];

@@ -51,6 +51,13 @@ __device__ __forceinline__ void tl_mark_one(int kid) {
 // and its writes are visible, griddep_launch() lets the successor's prologue begin. Both are no-ops otherwise.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Where a decode-chain kernel releases its PDL successor.  Early (0, at kernel entry): the successor's prologue and
+// weight prefetch overlap as much as possible, but every kernel of the chain that fits becomes resident and spins,
+// which starves the chains of OTHER batches in flight.  Late (1, once this kernel's own dependency is satisfied):
+// at most one waiting successor per chain is resident.
+__constant__ int g_pdl_late = 0;
+__device__ __forceinline__ void griddep_launch_early() { if (g_pdl_late == 0) griddep_launch(); }
+__device__ __forceinline__ void griddep_launch_late() { if (g_pdl_late != 0) griddep_launch(); }
 
 // Flag-based ordering of the decode-step kernel chain.  Kernel k of a step (launched with the PDL attribute, so
 // it may become resident while kernel k-1 still runs, but WITHOUT griddepcontrol.wait) spins until every CTA of

@@ -44,7 +44,7 @@ template <int D, bool PRE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   static_assert(D % 128 == 0, "D");
   constexpr int NV = D / 128;
-  griddep_launch();
+  griddep_launch_early();
   tl_mark(100002);
   const int lane = threadIdx.x & 31;
   // parameters are constants: fetch them before the dependency wait
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     griddep_wait();
     if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
   }
+  griddep_launch_late();
   tl_mark(2);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= p.rows) {
@@ -311,7 +312,7 @@ struct SelectParams {
 // grid (n_split, rows): each CTA folds one vocabulary slice of one row into (max, argmax, sum exp) with a
 // single online pass; the last CTA of a row combines the slices and does the reference's bookkeeping.
 __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p) {
-  griddep_launch();
+  griddep_launch_early();
   tl_mark(100005);
   StepState* st = p.state;
   if (p.chain.counters != nullptr) {
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
     griddep_wait();
     if (st->finished) return;
   }
+  griddep_launch_late();
   tl_mark(5);
   const int row = blockIdx.y;
   const int split = blockIdx.x;

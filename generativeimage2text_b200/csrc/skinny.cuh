@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t skinny_off(int rows, int row, int kchunk16) 
 
 __global__ void __launch_bounds__(256, 1) skinny_mma_kernel(const SkinnyParams p) {
   extern __shared__ __align__(128) uint8_t sk_smem[];
-  if (p.pdl) griddep_launch();
+  if (p.pdl) griddep_launch_early();
   if (p.pdl) tl_mark(100000 + 5000 + static_cast<int>(gridDim.x * gridDim.y));
   if ((!p.pdl || p.chain.counters != nullptr) && p.skip != nullptr && *p.skip != 0) return;
   const int tid = threadIdx.x;
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256, 1) skinny_mma_kernel(const SkinnyParams p
   cp_async_commit();
   if (p.chain.counters != nullptr) chain_wait(p.chain);
   else if (p.pdl) griddep_wait();
+  if (p.pdl) griddep_launch_late();
   if (p.pdl) tl_mark(5000 + static_cast<int>(gridDim.x * gridDim.y));
   // ---- activations (written by the predecessor: cp.async.cg reads through L2) ----
   for (int id = tid; id < kSkinnyRows * units; id += 256) {

@@ -133,7 +133,10 @@ class GitB200CaptioningModel(nn.Module):
             vocab=VOCAB, max_positions=MAX_POS, num_frames_emb=n_emb, sos_id=self.sos_index, eos_id=self.eos_index)
         # engine slots: slot 0 serves `model(batch)`; `submit()` round-robins over `n_slots` engines, each on its own
         # stream, so the encoder of one batch overlaps the latency-bound decode loop of the previous one
-        self.n_slots = 4
+        # (all slots share slot 0's device copy of the parameters: gitb200_share_weights)
+        import os
+        self.n_slots = max(1, min(8, int(os.environ.get('GITB200_SLOTS', '4'))))
+        self._options = {}
         self._slots = [dict(engine=None, sig=None, stream=None, pending=None) for _ in range(self.n_slots)]
         self._engine_device = None
         self._next_slot = 0
@@ -165,11 +168,22 @@ class GitB200CaptioningModel(nn.Module):
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
             sl['engine'], sl['sig'] = h, None
             import os
-            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'epi_direct', 'lanes', 'sm_reserve', 'decode_ctas'):
+            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'epi_direct', 'lanes', 'sm_reserve',
+                        'decode_ctas', 'prio_split', 'pdl_late'):
                 v = os.environ.get('GITB200_' + opt.upper())      # debugging switches, e.g. GITB200_USE_2CTA=0
                 if v is not None:
                     _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')
+            for opt, v in self._options.items():                  # set_engine_option() calls made so far
+                _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')
         sig = self._weights_signature()
+        if slot > 0:
+            # one device copy of the parameters: slot 0 owns it, the other slots borrow it
+            if self._slots[0]['engine'] is None or self._slots[0]['sig'] != sig:
+                self._ensure_engine(0)
+            if sl['sig'] is None:
+                _lib.check(lib.gitb200_share_weights(sl['engine'], self._slots[0]['engine']), sl['engine'], 'share_weights')
+            sl['sig'] = sig
+            return lib, stream
         if sig != sl['sig']:
             eng = sl['engine']
             for key, p in self.state_dict(keep_vars=True).items():
@@ -184,7 +198,7 @@ class GitB200CaptioningModel(nn.Module):
         return lib, stream
 
     def release(self):
-        for sl in self._slots:
+        for sl in reversed(self._slots):   # borrowers before the owner of the weights
             if sl['engine'] is not None:
                 _lib.load().gitb200_destroy(sl['engine'])
                 sl['engine'], sl['sig'], sl['pending'] = None, None, None
@@ -197,6 +211,7 @@ class GitB200CaptioningModel(nn.Module):
 
     def set_engine_option(self, name, value):
         """Engine switches: 'use_graph', 'use_pdl', 'use_chain' (0/1), 'lanes' (1..4 concurrent decode row groups)."""
+        self._options[name] = int(value)
         for k in range(self.n_slots):
             if k == 0 or self._slots[k]['engine'] is not None:
                 lib, _ = self._ensure_engine(k)

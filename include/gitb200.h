@@ -75,6 +75,11 @@ int gitb200_set_weight(gitb200_engine* h, const char* ref_key, const void* dev_p
                        int ndim, int dtype, void* stream);
 /* Checks that every tensor of the geometry has been provided. Synchronises the stream. */
 int gitb200_finalize_weights(gitb200_engine* h, void* stream);
+/* Several engines of one geometry on one device (one per batch in flight, see gitb200_generate_async) need only one
+ * copy of the parameters: `h` borrows the finalized weight buffers of `src` (which must outlive it) instead of taking
+ * its own gitb200_set_weight calls -- the module-level equivalent is calling one nn.Module from several threads.
+ * Keeps the decoder weights of all in-flight batches on the same L2 lines. */
+int gitb200_share_weights(gitb200_engine* h, gitb200_engine* src);
 
 /* Replaces: CaptioningModel.forward_one image branch = VisualTransformer.forward per frame
  * (+ img_temperal_embedding, token-axis concat)      layers/decoder.py:846-857, layers/CLIP/model.py:240-268.
@@ -130,7 +135,10 @@ int gitb200_generate_finish(gitb200_engine* h, int32_t* out_len_host);
 
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t gitb200_launch_count(const gitb200_engine* h);
-/* Enable/disable CUDA-graph replay of the decode step (default on). */
+/* Engine switches (defaults in parentheses): use_graph (1) CUDA-graph replay of the decode step, use_pdl (1), use_chain (1)
+ * flag-ordered decode chain, use_2cta (1), prio_split (0) decode loop on a high-priority stream, pdl_late (0, process-wide)
+ * release the PDL successor only once the kernel's own dependency is met, sm_reserve / decode_ctas (0) SM partitioning
+ * between batches in flight, lanes (1), use_lean (0), epi_direct (0). */
 int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value);
 
 /* ---- single-kernel entry points (unit tests, micro-benchmarks, ncu) -------------------------------- */

@@ -9,6 +9,7 @@ the bf16 GEMM noise.  So
   * the search semantics (no-repeat, EOS forcing, logprob normalisation, beam bookkeeping, hypothesis
     selection) are checked EXACTLY by replaying the oracle's search loop over the engine's own step logits.
 """
+import ctypes
 import numpy as np
 import pytest
 import torch
@@ -288,3 +289,34 @@ def test_pipelined_submit_matches_sync_calls():
     for a, b in zip(sync, outs):
         _same_captions(a, b)
     assert m.launch_count() > 0
+
+
+def test_engine_slots_share_one_weight_copy_and_scheduling_switches():
+    """All engine slots borrow slot 0's parameters (gitb200_share_weights); the scheduling switches used for batches in
+    flight (decode loop on a high-priority stream, late PDL release) do not change the captions."""
+    g = load_golden('base_greedy')
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    from generativeimage2text_b200.synthetic import synthetic_images
+    from generativeimage2text_b200 import _lib
+    m = _model(meta, sd, max_steps=12)
+    imgs = [synthetic_images(2, 0, 700 + i).cuda() for i in range(4)]
+    sync = [m({'image': x}) for x in imgs]
+    try:
+        for late, prio in ((1, 0), (0, 1), (1, 1)):
+            m.set_engine_option('pdl_late', late)
+            m.set_engine_option('prio_split', prio)
+            pend = [m.submit({'image': x}, depth=4) for x in imgs]
+            for a, p in zip(sync, pend):
+                _same_captions(a, p.result())
+        # a borrowing engine refuses its own parameters; its owner does not
+        lib = _lib.load()
+        eng1 = m._slots[1]['engine']
+        assert eng1 is not None
+        w = torch.zeros(768, device='cuda')
+        shape = (ctypes.c_int64 * 1)(768)
+        rc = lib.gitb200_set_weight(eng1, b'image_encoder.class_embedding', w.data_ptr(), shape, 1, _lib.F32, None)
+        assert rc != 0 and b'borrows' in lib.gitb200_last_error(eng1)
+    finally:
+        m.set_engine_option('pdl_late', 0)
+        m.set_engine_option('prio_split', 0)
