@@ -214,7 +214,13 @@ def main():
         previous result is collected, so its encoder overlaps the previous batch's latency-bound decode loop."""
         pend, toks = [], None
         for _ in range(k):
-            h = model.submit({'image': img_dev}, slot=None if depth > 1 else 0, depth=depth)
+            if depth == 1:     # the reference call: model(batch), one at a time on the caller's stream
+                out = model({'image': img_dev})
+                toks = out['predictions']
+                if world > 1:
+                    toks, _ = gather_captions(toks, out['logprobs'], n_total)
+                continue
+            h = model.submit({'image': img_dev}, depth=depth)
             pend.append(h)
             if len(pend) >= depth:
                 toks = finish_device(pend.pop(0))

@@ -258,10 +258,10 @@ class GitB200CaptioningModel(nn.Module):
         batch: {'image': FloatTensor[B,3,H,W] | [FloatTensor[B,3,H,W]] * frames, 'prefix'?: LongTensor[1,P]}
         forced_tokens / return_step_logits are parity-test hooks (teacher forcing, raw per-step logits).
         """
-        return self.submit(batch, forced_tokens, return_step_logits, slot=0).result()
+        return self.submit(batch, forced_tokens, return_step_logits, slot=0, _caller_stream=True).result()
 
     @torch.no_grad()
-    def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None, depth=2):
+    def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None, depth=2, _caller_stream=False):
         """Enqueue `model(batch)` without waiting: returns a handle whose `.result()` gives the reference's output
         dict.  Successive submits rotate over `depth` engines / streams (each engine: one call in flight)."""
         if self.training:
@@ -281,9 +281,11 @@ class GitB200CaptioningModel(nn.Module):
         eng = sl['engine']
         dev = self._device()
         cur = torch.cuda.current_stream(dev)
-        if slot == 0:
+        if _caller_stream:
             stream = cur                      # synchronous path: the caller's stream (stream 0 -> engine-owned stream)
         else:
+            # every slot on its own stream: work submitted earlier on the caller's stream must not order the batches in
+            # flight behind each other (only the inputs' producer is waited for)
             if sl['stream'] is None:
                 sl['stream'] = torch.cuda.Stream(device=dev)
             stream = sl['stream']

@@ -8,6 +8,7 @@ inputs) with `depth` batches in flight through model.submit().  Run on the GPU b
 import argparse
 import itertools
 import json
+import time
 import os
 import sys
 
@@ -45,7 +46,10 @@ def main():
     def run(k, depth):
         pend, out = [], None
         for _ in range(k):
-            pend.append(model.submit({'image': img}, slot=None if depth > 1 else 0, depth=depth))
+            if depth == 1:
+                out = model({'image': img})
+                continue
+            pend.append(model.submit({'image': img}, depth=depth))
             if len(pend) >= depth:
                 out = pend.pop(0).result()
         while pend:
@@ -70,23 +74,27 @@ def main():
         grid = [dict(pdl_late=l, prio_split=p, depth=d, sm_reserve=0, decode_ctas=0)
                 for l, p, d in itertools.product((0, 1), (0, 1), (1, 4))]
     else:
-        grid = []
+        grid = [dict(pdl_late=0, prio_split=0, depth=1, sm_reserve=0, decode_ctas=0)]
+        for reserve in (0, 32):                     # most informative first: the run may be cut short
+            for depth in (4, 6, 8):
+                for late, prio in itertools.product((0, 1), (0, 1)):
+                    grid.append(dict(pdl_late=late, prio_split=prio, depth=depth, sm_reserve=reserve, decode_ctas=0))
         for late, prio in itertools.product((0, 1), (0, 1)):
-            for depth in (1, 2, 4, 6, 8):
-                for reserve, dctas in ((0, 0), (16, 0), (32, 0), (0, 74), (32, 74)):
-                    if depth == 1 and (reserve or dctas or prio):
-                        continue
-                    grid.append(dict(pdl_late=late, prio_split=prio, depth=depth, sm_reserve=reserve, decode_ctas=dctas))
+            grid.append(dict(pdl_late=late, prio_split=prio, depth=4, sm_reserve=16, decode_ctas=100))
     ref = None
     rows = []
     for cfg in grid:
+        t0 = time.time()
         for k in ('pdl_late', 'prio_split', 'sm_reserve', 'decode_ctas'):
             model.set_engine_option(k, cfg[k])
+        t1 = time.time()
         ms, toks = timed(cfg['depth'])
+        t2 = time.time()
         if ref is None:
             ref = toks.clone()
         agree = float((toks == ref).all(dim=1).float().mean().item())
-        row = dict(cfg, ms_per_batch=round(ms, 3), captions_per_s=round(B / ms * 1e3, 1), same_captions=round(agree, 3))
+        row = dict(cfg, ms_per_batch=round(ms, 3), captions_per_s=round(B / ms * 1e3, 1), same_captions=round(agree, 3),
+                   host_s=[round(t1 - t0, 2), round(t2 - t1, 2)])
         rows.append(row)
         print(json.dumps(row), flush=True)
     best = max(rows, key=lambda r: r['captions_per_s'])
