@@ -239,16 +239,18 @@ def test_generate_host_and_tensor_vs_list_input():
 
 def _same_captions(a, b):
     """Two free-running runs of the same input. Split-K partial sums meet in fp32 atomics whose order differs from
-    run to run (~1e-5 relative on a logit), so a decision with a sub-noise margin may flip and the row then follows
-    a different continuation: require identical shapes, near-total token agreement, and matching logprobs on the
-    rows that did not fork."""
+    run to run; the sums are then rounded to bf16 GEMM operands, where a 1-ulp flip (2^-8 relative) moves a logit by
+    ~1e-3 (measured on B200: summed logprobs of identical 12-token captions differ by up to 2.2e-3 between runs). A
+    decision with a sub-noise margin may flip and the row then follows a different continuation: require identical
+    shapes, near-total token agreement, and logprobs within the bf16 noise band (1e-3 per step) on the rows that did
+    not fork."""
     pa, pb = a['predictions'], b['predictions']
     assert pa.shape == pb.shape
     same_rows = (pa == pb).all(dim=1)
     assert (pa == pb).float().mean().item() >= 0.75
     la, lb = a['logprobs'].reshape(-1), b['logprobs'].reshape(-1)
     if same_rows.any():
-        assert torch.allclose(la[same_rows], lb[same_rows], atol=2e-3)
+        assert torch.allclose(la[same_rows], lb[same_rows], atol=1e-3 * max(pa.shape[1], 10))
 
 
 def test_decode_lanes_match_single_lane():
