@@ -5,7 +5,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libgitb200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int, c_int64, c_float, c_char_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_char_p
 c_ll = ctypes.c_longlong
@@ -22,6 +22,13 @@ class Search(ctypes.Structure):
                 ('per_node_beam', ctypes.c_int32), ('length_penalty', ctypes.c_float)]
 
 
+class ImageDesc(ctypes.Structure):
+    _fields_ = [('src_offset', ctypes.c_int64), ('src_h', ctypes.c_int32), ('src_w', ctypes.c_int32),
+                ('resize_h', ctypes.c_int32), ('resize_w', ctypes.c_int32), ('crop_top', ctypes.c_int32),
+                ('crop_left', ctypes.c_int32), ('out_h', ctypes.c_int32), ('out_w', ctypes.c_int32),
+                ('dst_offset', ctypes.c_int64)]
+
+
 SEARCH_GREEDY, SEARCH_BEAM = 0, 1
 F32, BF16, I64 = 0, 1, 2
 
@@ -34,6 +41,7 @@ SIGNATURES = {
     'gitb200_set_weight': (c_int, [c_void_p, c_char_p, c_void_p, ctypes.POINTER(c_int64), c_int, c_int, c_void_p]),
     'gitb200_finalize_weights': (c_int, [c_void_p, c_void_p]),
     'gitb200_share_weights': (c_int, [c_void_p, c_void_p]),
+    'gitb200_set_input_size': (c_int, [c_void_p, c_int, c_int]),
     'gitb200_encode': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'gitb200_prefill': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'gitb200_decode_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -48,6 +56,13 @@ SIGNATURES = {
     'gitb200_generate_finish': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_int32)]),
     'gitb200_launch_count': (c_int64, [c_void_p]),
     'gitb200_set_option': (c_int, [c_void_p, c_char_p, c_int64]),
+    'gitb200_preproc_create': (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    'gitb200_preproc_destroy': (None, [c_void_p]),
+    'gitb200_preproc_last_error': (c_char_p, [c_void_p]),
+    'gitb200_preproc_launch_count': (c_int64, [c_void_p]),
+    'gitb200_preproc_run': (c_int, [c_void_p, c_void_p, c_int64, c_int, ctypes.POINTER(ImageDesc), c_int,
+                                    ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_int64, c_void_p]),
+    'gitb200_preproc_coeffs': (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_void_p, c_void_p, c_int]),
     'gitb200_debug_timeline': (c_int, [c_int, c_void_p, c_int]),
     'gitb200_op_gemm': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),

@@ -30,6 +30,7 @@
 #include "attention.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "preproc.cuh"
 #include "ptx.cuh"
 #include "rowops.cuh"
 #include "search.cuh"
@@ -38,7 +39,7 @@
 using namespace gitb200;
 typedef __nv_bfloat16 bf16;
 
-#define GITB200_ABI_VERSION 2
+#define GITB200_ABI_VERSION 3
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -126,6 +127,9 @@ struct gitb200_engine {
 
   // derived geometry
   int g = 0, L = 0, Kpatch = 0, Kp = 0, d = 0, D = 0, F = 0, V = 0;
+  // input size of the next encode (gitb200_set_input_size; default image_size x image_size): patch grid gh x gw,
+  // Lc = gh * gw + 1 tokens per image; differs from (g, g, L) for MinMaxResizeForTest inputs (reference inference.py:29-64)
+  int in_h = 0, in_w = 0, gh = 0, gw = 0, Lc = 0;
 
   // weights
   DevBuf w_patch, cls, pos_emb, lnpre_g, lnpre_b, lnpost_g, lnpost_b;
@@ -136,7 +140,7 @@ struct gitb200_engine {
   bool finalized = false;
 
   // workspaces
-  DevBuf x, h, qkv, ctx, u, feats, feats_f32;               // encoder
+  DevBuf x, h, qkv, ctx, u, feats, feats_f32, pos_interp;   // encoder
   DevBuf pt, pxd, phd, pq, pctx, pu;                        // prefill
   DevBuf img_kv, txt_kv, src_row[2];                        // caches
   DevBuf xd_t, hd_t, qkv_t, ctx_t, t_t, u_t, logits;        // decode step
@@ -590,6 +594,21 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   return fail(h, "unknown option %s", name);
 }
 
+extern "C" int gitb200_set_input_size(gitb200_engine* h, int height, int width) {
+  if (!h) return 1;
+  if (h->pending) return fail(h, "set_input_size: a generate call is in flight");
+  const int p = h->cfg.patch;
+  if (height < p || width < p) return fail(h, "set_input_size: %dx%d is smaller than one %dx%d patch", height, width, p, p);
+  const long long tokens = static_cast<long long>(height / p) * (width / p) + 1;
+  if (tokens > 16384) return fail(h, "set_input_size: %dx%d gives %lld tokens per image (limit 16384)", height, width, tokens);
+  h->in_h = height;
+  h->in_w = width;
+  h->gh = height / p;      // nn.Conv2d(kernel = stride = patch, no padding) drops a trailing partial patch
+  h->gw = width / p;
+  h->Lc = h->gh * h->gw + 1;
+  return 0;
+}
+
 extern "C" int gitb200_create(const gitb200_config* cfg, int device, gitb200_engine** out) {
   gitb200_engine* h = nullptr;
   if (!cfg || !out) return fail(nullptr, "gitb200_create: null argument");
@@ -612,6 +631,9 @@ extern "C" int gitb200_create(const gitb200_config* cfg, int device, gitb200_eng
   h->num_sms = prop.multiProcessorCount;
   h->g = cfg->image_size / cfg->patch;
   h->L = h->g * h->g + 1;
+  h->in_h = h->in_w = cfg->image_size;
+  h->gh = h->gw = h->g;
+  h->Lc = h->L;
   h->Kpatch = 3 * cfg->patch * cfg->patch;
   h->Kp = (h->Kpatch + 63) / 64 * 64;
   h->d = cfg->enc_width;
@@ -628,7 +650,7 @@ extern "C" int gitb200_create(const gitb200_config* cfg, int device, gitb200_eng
 static void release_all(gitb200_engine* h) {
   DevBuf* bufs[] = {&h->w_patch, &h->cls, &h->pos_emb, &h->lnpre_g, &h->lnpre_b, &h->lnpost_g, &h->lnpost_b, &h->w_vp,
                     &h->b_vp, &h->lnvp_g, &h->lnvp_b, &h->words_f32, &h->words_bf16, &h->positions, &h->lnemb_g,
-                    &h->lnemb_b, &h->out_bias, &h->temb, &h->x, &h->h, &h->qkv, &h->ctx, &h->u, &h->feats, &h->feats_f32,
+                    &h->lnemb_b, &h->out_bias, &h->temb, &h->x, &h->h, &h->qkv, &h->ctx, &h->u, &h->feats, &h->feats_f32, &h->pos_interp,
                     &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->txt_kv, &h->src_row[0],
                     &h->src_row[1], &h->xd_t, &h->hd_t, &h->qkv_t, &h->ctx_t, &h->t_t, &h->u_t, &h->logits, &h->state,
                     &h->next_token, &h->logprob_sum, &h->tokens_i64, &h->stage_img, &h->stage_tok, &h->stage_lp,
@@ -862,14 +884,14 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
     // reference zip() truncates to the number of temporal embeddings (layers/decoder.py:848-849)
     frames = h->cfg.num_frames_emb;
   }
-  const int d = h->d, L = h->L, g = h->g, Kp = h->Kp, H = h->cfg.enc_heads;
+  const int d = h->d, L = h->Lc, gh = h->gh, gw = h->gw, Kp = h->Kp, H = h->cfg.enc_heads;
   const int NI = B * frames;
   const long long Me = static_cast<long long>(NI) * L;
   CK(h->x.ensure(Me * d * 4));
   CK(h->h.ensure(Me * d * 2));
   CK(h->qkv.ensure(Me * 3 * d * 2));
   CK(h->ctx.ensure(Me * d * 2));
-  CK(h->u.ensure(std::max<long long>(Me * 4 * d * 2, static_cast<long long>(NI) * g * g * Kp * 2)));
+  CK(h->u.ensure(std::max<long long>(Me * 4 * d * 2, static_cast<long long>(NI) * gh * gw * Kp * 2)));
   CK(h->feats.ensure(Me * d * 2));
   float* x = h->x.as<float>();
   bf16* hb = h->h.as<bf16>();
@@ -877,22 +899,33 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
   bf16* ctx = h->ctx.as<bf16>();
   bf16* u = h->u.as<bf16>();
 
+  // positional embedding of this input size: the stored one, or its bicubic re-sampling to the gh x gw grid
+  // (reference layers/CLIP/model.py:245-251; recomputed per call: 1 + gh*gw rows, the parameters may have changed)
+  const float* pos = h->pos_emb.as<float>();
+  if (gh != h->g || gw != h->g) {
+    CK(h->pos_interp.ensure(static_cast<size_t>(L) * d * 4));
+    const long long total = static_cast<long long>(L) * (d / 4);
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 8));
+    pos_embed_bicubic_kernel<<<grid, 256, 0, st>>>(h->pos_emb.as<float>(), h->pos_interp.as<float>(), h->g, gh, gw, d);
+    CKL(h, "pos_embed_bicubic_kernel");
+    pos = h->pos_interp.as<float>();
+  }
   // patch embedding: im2col + GEMM, rows land at token index 1 + patch (CLS row is filled by the next kernel)
   {
-    const long long total = static_cast<long long>(NI) * g * g * (Kp / 8);
+    const long long total = static_cast<long long>(NI) * gh * gw * (Kp / 8);
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 16));
-    im2col_patch_kernel<<<grid, 256, 0, st>>>(images, u, NI, h->cfg.image_size, h->cfg.patch, g, Kp);
+    im2col_patch_kernel<<<grid, 256, 0, st>>>(images, u, NI, h->in_h, h->in_w, h->cfg.patch, gh, gw, Kp);
     CKL(h, "im2col_patch_kernel");
-    GemmCall c = gemm_plain(u, Kp, h->w_patch.as<bf16>(), Kp, NI * g * g, d, Kp, nullptr, ACT_NONE, nullptr, x, false);
-    c.p.rows_per_batch = g * g;
+    GemmCall c = gemm_plain(u, Kp, h->w_patch.as<bf16>(), Kp, NI * gh * gw, d, Kp, nullptr, ACT_NONE, nullptr, x, false);
+    c.p.rows_per_batch = gh * gw;
     c.p.batch_stride = L;
     c.p.row_offset = 1;
     TRY(launch_gemm(h, c, st));
     const int gridr = static_cast<int>((Me + 7) / 8);
     if (d == 768)
-      cls_pos_lnpre_kernel<768><<<gridr, 256, 0, st>>>(x, h->cls.as<float>(), h->pos_emb.as<float>(), h->lnpre_g.as<float>(), h->lnpre_b.as<float>(), static_cast<int>(Me), L);
+      cls_pos_lnpre_kernel<768><<<gridr, 256, 0, st>>>(x, h->cls.as<float>(), pos, h->lnpre_g.as<float>(), h->lnpre_b.as<float>(), static_cast<int>(Me), L);
     else
-      cls_pos_lnpre_kernel<1024><<<gridr, 256, 0, st>>>(x, h->cls.as<float>(), h->pos_emb.as<float>(), h->lnpre_g.as<float>(), h->lnpre_b.as<float>(), static_cast<int>(Me), L);
+      cls_pos_lnpre_kernel<1024><<<gridr, 256, 0, st>>>(x, h->cls.as<float>(), pos, h->lnpre_g.as<float>(), h->lnpre_b.as<float>(), static_cast<int>(Me), L);
     CKL(h, "cls_pos_lnpre_kernel");
   }
   for (int i = 0; i < h->cfg.enc_layers; ++i) {
@@ -1123,3 +1156,4 @@ static int set_attn_smem_limit(gitb200_engine* h) {
 }
 
 #include "engine_api.inc"
+#include "preproc_api.inc"

@@ -149,17 +149,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
 
 // Patch im2col for the stride==kernel conv (reference layers/CLIP/model.py:224,242):
 // A[(img, py, px)][(c, ky, kx)] = img[c, py*p+ky, px*p+kx], zero-padded to Kp columns, bf16.
-__global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int n_img, int S,
-                                    int p, int g, int Kp) {
-  const long long total = static_cast<long long>(n_img) * g * g * (Kp / 8);
+__global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int n_img, int H, int W,
+                                    int p, int gh, int gw, int Kp) {
+  const long long total = static_cast<long long>(n_img) * gh * gw * (Kp / 8);
   const int K = 3 * p * p;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int kc = static_cast<int>(idx % (Kp / 8));
     const long long row = idx / (Kp / 8);
-    const int px = static_cast<int>(row % g);
-    const int py = static_cast<int>((row / g) % g);
-    const long long im = row / (g * g);
+    const int px = static_cast<int>(row % gw);
+    const int py = static_cast<int>((row / gw) % gh);
+    const long long im = row / (gh * gw);
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -170,7 +170,7 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16
         const int r = k - c * p * p;
         const int ky = r / p;
         const int kx = r - ky * p;
-        x = __ldg(img + ((im * 3 + c) * S + (py * p + ky)) * static_cast<long long>(S) + (px * p + kx));
+        x = __ldg(img + ((im * 3 + c) * H + (py * p + ky)) * static_cast<long long>(W) + (px * p + kx));
       }
       v[j] = x;
     }
@@ -180,6 +180,57 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16
     o.z = pack_bf16(v[4], v[5]);
     o.w = pack_bf16(v[6], v[7]);
     reinterpret_cast<uint4*>(A + row * Kp)[kc] = o;
+  }
+}
+
+// Positional embedding [1 + g0*g0, d] re-sampled to a gh x gw grid for inputs whose size differs from the resolution the
+// embedding was built for (reference layers/CLIP/model.py:245-251): CLS row copied, grid rows =
+// F.interpolate(mode='bicubic', align_corners=False), i.e. source coordinate (o + 0.5) * in / out - 0.5, Keys cubic with
+// A = -0.75 over taps floor(x) - 1 .. floor(x) + 2 clamped to the grid. One thread per (token, 4 channels).
+__device__ __forceinline__ void cubic_coeffs_a075(float t, float w[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.0f, x1 = t, x2 = 1.0f - t, x3 = 2.0f - t;
+  w[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+  w[1] = ((A + 2.0f) * x1 - (A + 3.0f)) * x1 * x1 + 1.0f;
+  w[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
+  w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+__global__ void __launch_bounds__(256)
+pos_embed_bicubic_kernel(const float* __restrict__ pos, float* __restrict__ out, int g0, int gh, int gw, int d) {
+  const int d4 = d >> 2;
+  const long long total = static_cast<long long>(1 + gh * gw) * d4;
+  const float sy = static_cast<float>(g0) / static_cast<float>(gh), sx = static_cast<float>(g0) / static_cast<float>(gw);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % d4);
+    const int tok = static_cast<int>(idx / d4);
+    const float4* src = reinterpret_cast<const float4*>(pos);
+    float4 acc;
+    if (tok == 0) {
+      acc = __ldg(src + c);
+    } else {
+      const int oy = (tok - 1) / gw, ox = (tok - 1) - oy * gw;
+      const float ry = sy * (oy + 0.5f) - 0.5f, rx = sx * (ox + 0.5f) - 0.5f;
+      const float fy = floorf(ry), fx = floorf(rx);
+      float wy[4], wx[4];
+      cubic_coeffs_a075(ry - fy, wy);
+      cubic_coeffs_a075(rx - fx, wx);
+      const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int yy = min(max(iy - 1 + a, 0), g0 - 1);
+        float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int xx = min(max(ix - 1 + b, 0), g0 - 1);
+          const float4 v = __ldg(src + static_cast<long long>(1 + yy * g0 + xx) * d4 + c);
+          row.x += wx[b] * v.x; row.y += wx[b] * v.y; row.z += wx[b] * v.z; row.w += wx[b] * v.w;
+        }
+        acc.x += wy[a] * row.x; acc.y += wy[a] * row.y; acc.z += wy[a] * row.z; acc.w += wy[a] * row.w;
+      }
+    }
+    reinterpret_cast<float4*>(out)[idx] = acc;
   }
 }
 

@@ -238,16 +238,18 @@ class GitB200CaptioningModel(nn.Module):
             frames = len(image)
             ims = [im.to(device=dev, dtype=torch.float32) for im in image]
             B = ims[0].shape[0]
+            if any(im.shape != ims[0].shape for im in ims):
+                raise ValueError('all frames of a batch must share one size')
             x = ims[0].contiguous() if frames == 1 else torch.stack(ims, dim=0).contiguous()
         else:
             frames = 0
             x = image.to(device=dev, dtype=torch.float32).contiguous()
             B = x.shape[0]
-        S = self.image_size
-        if tuple(x.shape[-3:]) != (3, S, S):
-            raise NotImplementedError(
-                'input resolution %s != %d: runtime positional-embedding interpolation (reference '
-                'layers/CLIP/model.py:245-251) is not implemented' % (tuple(x.shape[-2:]), S))
+        if x.dim() != (4 if frames <= 1 else 5) or x.shape[-3] != 3:
+            raise ValueError('images must be [B, 3, H, W] tensors (got %s)' % (tuple(x.shape),))
+        enc = ENCODER_CFG[self.param.get('image_encoder_type', 'CLIPViT_B_16')]
+        if x.shape[-2] < enc['patch'] or x.shape[-1] < enc['patch']:
+            raise ValueError('input %s is smaller than one patch' % (tuple(x.shape[-2:]),))
         return x, B, frames
 
     # ---------------------------------------------------------------- the reference surface
@@ -312,6 +314,9 @@ class GitB200CaptioningModel(nn.Module):
         for t in (x, prefix, forced):
             if t is not None and stream is not cur:
                 t.record_stream(stream)
+        # inputs of another size than test_crop_size (MinMaxResizeForTest, reference inference.py:29-64): the engine
+        # re-samples the positional embedding to their patch grid (reference layers/CLIP/model.py:245-251)
+        _lib.check(lib.gitb200_set_input_size(eng, int(x.shape[-2]), int(x.shape[-1])), eng, 'set_input_size')
         _lib.check(lib.gitb200_generate_async(
             eng, x.data_ptr(), B, frames, prefix.data_ptr() if prefix is not None else None, P,
             ctypes.byref(sp), forced.data_ptr() if forced is not None else None, tokens.data_ptr(),
@@ -355,7 +360,8 @@ class GitB200CaptioningModel(nn.Module):
         lib, stream = self._ensure_engine()
         x, B, frames = self._pack_images(image)
         enc = ENCODER_CFG[self.param.get('image_encoder_type', 'CLIPViT_B_16')]
-        L = (self.image_size // enc['patch']) ** 2 + 1
+        L = (x.shape[-2] // enc['patch']) * (x.shape[-1] // enc['patch']) + 1
+        _lib.check(lib.gitb200_set_input_size(self._engine, int(x.shape[-2]), int(x.shape[-1])), self._engine, 'set_input_size')
         nf = max(frames, 1)
         if frames and self.num_image_with_embedding:
             nf = min(nf, self.num_image_with_embedding)

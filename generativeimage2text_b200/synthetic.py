@@ -152,10 +152,12 @@ def synthetic_state_dict(param=None, seed=0, variant='init'):
 
 def synthetic_images(batch, frames=0, seed=1234, res=224):
     """Synthetic CLIP-normalised pixels: one fp32 [B,3,res,res] tensor (frames=0) or a list of
-    `frames` such tensors (video path, reference inference.py:89 passes a list)."""
+    `frames` such tensors (video path, reference inference.py:89 passes a list).  `res` may be (height, width)."""
+    rh, rw = (res, res) if isinstance(res, int) else (int(res[0]), int(res[1]))
+
     def one(i):
         g = np.random.Generator(np.random.PCG64([int(seed), int(i)]))
-        return torch.from_numpy(g.standard_normal((batch, 3, res, res), dtype=np.float32))
+        return torch.from_numpy(g.standard_normal((batch, 3, rh, rw), dtype=np.float32))
     if not frames:
         return one(0)
     return [one(i) for i in range(frames)]

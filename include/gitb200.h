@@ -83,10 +83,18 @@ int gitb200_share_weights(gitb200_engine* h, gitb200_engine* src);
 
 /* Replaces: CaptioningModel.forward_one image branch = VisualTransformer.forward per frame
  * (+ img_temperal_embedding, token-axis concat)      layers/decoder.py:846-857, layers/CLIP/model.py:240-268.
- * images_dev: fp32 [frames][B,3,S,S] contiguous (frames >= 1; frame f at offset f*B*3*S*S).
+ * images_dev: fp32 [frames][B,3,H,W] contiguous (frames >= 1; frame f at offset f*B*3*H*W; H = W = image_size unless
+ * gitb200_set_input_size says otherwise).
  * feats_out_dev: fp32 [B, frames*L, enc_width] or NULL (kept internally for gitb200_prefill). */
 int gitb200_encode(gitb200_engine* h, const float* images_dev, int batch, int frames, float* feats_out_dev,
                    void* stream);
+
+/* Input size of the following gitb200_encode / gitb200_generate* calls when it differs from image_size x image_size
+ * (MinMaxResizeForTest inputs, inference.py:29-64): the patch grid becomes (height / patch) x (width / patch) and the
+ * positional embedding is re-sampled to it on the device, bicubic, as VisualTransformer.forward does at run time
+ *                                                                                  layers/CLIP/model.py:245-251.
+ * All images of one call share the size.  Sticky until changed; gitb200_create starts at image_size x image_size. */
+int gitb200_set_input_size(gitb200_engine* h, int height, int width);
 
 /* Replaces: visual_projection + the image rows of BertEncoderAsDecoder, computed once (KV cache)
  *                                      layers/decoder.py:535, 92-174; layers/bert/modeling_bert.py:92-334.
@@ -160,6 +168,38 @@ int gitb200_op_attention(const void* q_dev, const void* k_dev, const void* v_dev
                          long long q_row_stride, long long kv_row_stride, long long q_batch_stride,
                          long long kv_batch_stride, long long out_row_stride, long long out_batch_stride,
                          void* stream);
+
+/* ---- test-time image transform on the GPU ----------------------------------------------------------------
+ * Replaces: get_image_transform(param)(pil_image)                                       inference.py:111-132
+ *   = torchvision Resize(crop, BICUBIC) -> CenterCrop(crop) -> ToTensor -> Normalize(CLIP mean/std), or, with
+ *   param['test_respect_ratio_max'], MinMaxResizeForTest                                inference.py:29-64
+ * applied to DECODED images (uint8 RGB, HWC -- what PIL's Image.convert('RGB') holds).  Results are bit-identical to
+ * the PIL / torchvision pipeline (Pillow's two-pass fixed-point bicubic with antialiasing, libImaging/Resample.c).
+ * The caller computes the size rule (it is host arithmetic on two integers, see generativeimage2text_b200/inference.py)
+ * and passes one descriptor per image; images of one call may all differ in size. */
+typedef struct gitb200_preproc gitb200_preproc;
+typedef struct gitb200_image_desc {
+  int64_t src_offset;      /* bytes: first pixel of this image inside the packed source buffer                    */
+  int32_t src_h, src_w;    /* decoded size                                                                        */
+  int32_t resize_h, resize_w; /* size after the bicubic resize (== src: that axis is not resampled)               */
+  int32_t crop_top, crop_left; /* window of the resized image that is produced (CenterCrop; 0,0 + full size = none) */
+  int32_t out_h, out_w;
+  int64_t dst_offset;      /* fp32 elements: the image lands as [3, out_h, out_w] at out_dev + dst_offset          */
+} gitb200_image_desc;
+
+int gitb200_preproc_create(int device, gitb200_preproc** out);
+void gitb200_preproc_destroy(gitb200_preproc* p);
+const char* gitb200_preproc_last_error(const gitb200_preproc* p);
+int64_t gitb200_preproc_launch_count(const gitb200_preproc* p);
+/* src: packed uint8 RGB images, on the device (src_on_host == 0) or in host memory (pinned or pageable; copied to the
+ * device on `stream` first).  mean3 / std3: host float[3].  Work is enqueued on `stream`; a second call on the same
+ * handle first waits (on the host) for the previous call's kernels, so use one handle per stream to overlap calls. */
+int gitb200_preproc_run(gitb200_preproc* p, const uint8_t* src, int64_t src_bytes, int src_on_host,
+                        const gitb200_image_desc* descs_host, int n, const float* mean3, const float* std3,
+                        float* out_dev, int64_t out_elems, void* stream);
+/* Host-only helper (no GPU needed): the fixed-point weight table of one axis, i.e. Resample.c precompute_coeffs +
+ * normalize_coeffs_8bpc for BICUBIC: bounds_out int32 [out_size][2] (first tap, taps), kk_out int32 [out_size][kk_cap]. */
+int gitb200_preproc_coeffs(int in_size, int out_size, int32_t* ksize_out, int32_t* bounds_out, int32_t* kk_out, int kk_cap);
 
 /* Debug aid: in-situ timeline of the decode-step kernels. enable != 0 arms it; enable == 0 copies up to
  * max_entries (globaltimer ns, kernel id) pairs to out_host, disarms, and returns the number of entries. */

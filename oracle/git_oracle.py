@@ -49,12 +49,15 @@ def encode_image(sd, param, img, taps=None):
     pre = 'image_encoder.'
     B = img.shape[0]
     x = F.conv2d(img, sd[pre + 'conv1.weight'], None, stride=p)                # :242
-    g = x.shape[2]
-    assert x.shape[2] * x.shape[3] + 1 == sd[pre + 'positional_embedding'].shape[0], \
-        'runtime pos-embed interpolation (:245-251) is out of scope (SURVEY.md section 8f-2)'
+    pos = sd[pre + 'positional_embedding']
+    g0 = int(round(math.sqrt(pos.shape[0] - 1)))                                # expected_dim :243
+    if x.shape[2] != g0 or x.shape[3] != g0:                                    # :245-251 run-time re-sampling
+        grid = pos[1:, :].reshape(g0, g0, d).permute(2, 0, 1).unsqueeze(0)
+        grid = F.interpolate(grid, size=(x.shape[2], x.shape[3]), mode='bicubic')
+        pos = torch.cat((pos[0:1, :], grid.squeeze(0).permute(1, 2, 0).reshape(-1, d)), dim=0)
     x = x.reshape(B, d, -1).permute(0, 2, 1)                                  # :252-253
     cls = sd[pre + 'class_embedding'].expand(B, 1, d)
-    x = torch.cat([cls, x], dim=1) + sd[pre + 'positional_embedding']         # :254-255
+    x = torch.cat([cls, x], dim=1) + pos                                      # :254-255
     x = _ln(x, sd, pre + 'ln_pre', 1e-5)                                      # :257
     if taps is not None:
         taps['ln_pre'] = x

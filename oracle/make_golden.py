@@ -40,6 +40,13 @@ CASES = {
                          search='greedy', max_steps=16),
     'large_greedy': dict(param=LARGE, variant='perturbed', batch=1, frames=0, search='greedy', max_steps=12),
     'large_beam': dict(param=LARGE, variant='init', batch=1, frames=0, search='beam', max_steps=12),
+    # MinMaxResizeForTest-style input: a 160-crop model (10x10 grid embedding) fed 160x208 pixels (10x13 grid) ->
+    # run-time positional-embedding interpolation (reference layers/CLIP/model.py:245-251)
+    'base_ratio_greedy': dict(param={'test_crop_size': 160, 'test_respect_ratio_max': 224}, variant='perturbed', batch=2,
+                              frames=0, search='greedy', max_steps=12, image_hw=[160, 208]),
+    # square non-default crop: the embedding is built for the 10x10 grid, no run-time interpolation
+    'base_crop160_greedy': dict(param={'test_crop_size': 160}, variant='perturbed', batch=2, frames=1, search='greedy',
+                                max_steps=12, image_hw=[160, 160]),
 }
 
 
@@ -51,7 +58,7 @@ def vocab_sample():
 def run_case(name, cfg, seed=0, img_seed=1234):
     sd = synthetic_state_dict(cfg['param'], seed, cfg['variant'])
     model = ref_shim.load_reference_model(cfg['param'], cfg['search'], cfg['max_steps'], state_dict=sd)
-    image = synthetic_images(cfg['batch'], cfg['frames'], img_seed)
+    image = synthetic_images(cfg['batch'], cfg['frames'], img_seed, cfg.get('image_hw', 224))
     batch = {'image': image}
     if 'prefix' in cfg:
         batch['prefix'] = torch.tensor([cfg['prefix']], dtype=torch.long)

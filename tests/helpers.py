@@ -18,7 +18,7 @@ def load_golden(name):
 def golden_inputs(meta):
     from generativeimage2text_b200.synthetic import synthetic_state_dict, synthetic_images
     sd = synthetic_state_dict(meta['param'], meta['seed'], meta['variant'])
-    image = synthetic_images(meta['batch'], meta['frames'], meta['img_seed'])
+    image = synthetic_images(meta['batch'], meta['frames'], meta['img_seed'], meta.get('image_hw', 224))
     batch = {'image': image}
     if 'prefix' in meta:
         batch['prefix'] = torch.tensor([meta['prefix']], dtype=torch.long)

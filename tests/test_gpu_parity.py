@@ -50,7 +50,7 @@ def _to_cuda(batch):
     return out
 
 
-@pytest.mark.parametrize('name', ['base_greedy', 'vatex_greedy', 'large_greedy'])
+@pytest.mark.parametrize('name', ['base_greedy', 'vatex_greedy', 'large_greedy', 'base_ratio_greedy', 'base_crop160_greedy'])
 def test_image_features_and_projection(name):
     g = load_golden(name)
     meta = g['meta']
@@ -72,7 +72,8 @@ def test_image_features_and_projection(name):
     np.testing.assert_allclose(vproj.cpu()[:, ::17, ::29].numpy(), g['vproj_sample'], rtol=0, atol=0.15)
 
 
-@pytest.mark.parametrize('name', ['base_greedy_init', 'base_greedy', 'base_prefix', 'vatex_greedy', 'large_greedy'])
+@pytest.mark.parametrize('name', ['base_greedy_init', 'base_greedy', 'base_prefix', 'vatex_greedy', 'large_greedy',
+                                  'base_ratio_greedy', 'base_crop160_greedy'])
 def test_greedy_teacher_forced_against_reference(name):
     g = load_golden(name)
     meta = g['meta']
