@@ -261,6 +261,60 @@ def test_git_inference_single_image(image_path, model_name, prefix, tokenizer=No
     return cap
 
 
+def write_rows_sharded(rows, out_tsv, rank=None, world_size=None, poll_s=0.2):
+    """Write this rank's prediction rows and merge the ranks' parts into `out_tsv` (row order = rank order, as the
+    rows were sharded by `shard_range`).  Returns the number of rows this rank produced.
+
+    * one process: rows go straight to `out_tsv` (reference inference.py:163-164, 212);
+    * `torch.distributed` initialised: ONE gather of the finished rows to rank 0, which writes `out_tsv`;
+    * ranks without a process group (plain mpirun, as the reference is launched): the reference's scheme
+      (inference.py:159-162, 213-225) -- every rank writes `{out_tsv}.{rank}.{world}.tsv`, rank 0 waits for all parts
+      and concatenates them -- except that a part appears under its final name only once complete."""
+    rank = get_mpi_rank() if rank is None else rank
+    world_size = get_mpi_size() if world_size is None else world_size
+    if world_size <= 1:
+        n = 0
+
+        def counted():
+            nonlocal n
+            for r in rows:
+                n += 1
+                yield r
+        tsv_writer(counted(), out_tsv)
+        return n
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        mine = list(rows)
+        gathered = [None] * world_size if rank == 0 else None
+        torch.distributed.gather_object(mine, gathered, dst=0)
+        if rank == 0:
+            tsv_writer((r for part in gathered for r in part), out_tsv)
+        return len(mine)
+
+    def part(r):
+        return '{}.{}.{}.tsv'.format(out_tsv, r, world_size)
+    n = 0
+
+    def counted():
+        nonlocal n
+        for r in rows:
+            n += 1
+            yield r
+    tmp = part(rank)[:-4] + '.partial.tsv'
+    tsv_writer(counted(), tmp)
+    for ext in ('.lineidx', '.lineidx.8b', '.tsv'):      # the .tsv last: it is what rank 0 polls for
+        os.replace(op.splitext(tmp)[0] + ext, op.splitext(part(rank))[0] + ext)
+    if rank == 0:
+        parts = [part(i) for i in range(world_size)]
+        while True:
+            not_ready = [t for t in parts if not op.isfile(t)]
+            if not not_ready:
+                break
+            logging.info('waiting {}'.format(','.join(not_ready)))
+            time.sleep(poll_s)
+        concat_tsv_files(parts, out_tsv)
+    return n
+
+
 def test_git_inference_single_tsv(image_tsv, model_name, question_tsv, out_tsv, tokenizer=None, checkpoint=None,
                                   param=None, batch_size=64, depth=4, decode_workers=8, model=None):
     """reference inference.py:134-225, batched (see module docstring).  Returns the number of rows this rank wrote."""
@@ -280,10 +334,6 @@ def test_git_inference_single_tsv(image_tsv, model_name, question_tsv, out_tsv, 
 
     rank, world_size = get_mpi_rank(), get_mpi_size()
 
-    def get_rank_specific_tsv(r):
-        return '{}.{}.{}.tsv'.format(out_tsv, r, world_size)
-    dist_on = world_size > 1 and torch.distributed.is_available() and torch.distributed.is_initialized()
-    curr_out_tsv = get_rank_specific_tsv(rank) if (world_size > 1 and not dist_on) else out_tsv
     curr_start, curr_end = shard_range(len(image_tsv), rank, world_size)
     pool = ThreadPoolExecutor(max_workers=max(1, decode_workers))
 
@@ -329,39 +379,7 @@ def test_git_inference_single_tsv(image_tsv, model_name, question_tsv, out_tsv, 
 
     gen_rows = question_rows if question_tsv else caption_rows
     with torch.no_grad():
-        if dist_on:
-            rows = list(gen_rows())
-            gathered = [None] * world_size if rank == 0 else None
-            torch.distributed.gather_object(rows, gathered, dst=0)
-            if rank == 0:
-                tsv_writer((r for part in gathered for r in part), out_tsv)
-            n_rows = len(rows)
-        else:
-            n_rows = 0
-
-            def counted():
-                nonlocal n_rows
-                for r in gen_rows():
-                    n_rows += 1
-                    yield r
-            if world_size > 1:
-                # a part becomes visible under its final name only when complete (the reference polls for the
-                # bare file, inference.py:215-222, which exists from the first row on)
-                tmp = curr_out_tsv[:-4] + '.partial.tsv'
-                tsv_writer(counted(), tmp)
-                for ext in ('.lineidx', '.lineidx.8b', '.tsv'):
-                    os.replace(op.splitext(tmp)[0] + ext, op.splitext(curr_out_tsv)[0] + ext)
-            else:
-                tsv_writer(counted(), curr_out_tsv)
-            if world_size > 1 and rank == 0:
-                all_sub_tsv = [get_rank_specific_tsv(i) for i in range(world_size)]
-                while True:
-                    not_ready = [t for t in all_sub_tsv if not op.isfile(t)]
-                    if len(not_ready) == 0:
-                        break
-                    logging.info('waiting {}'.format(','.join(not_ready)))
-                    time.sleep(0.2)
-                concat_tsv_files(all_sub_tsv, out_tsv)
+        n_rows = write_rows_sharded(gen_rows(), out_tsv, rank, world_size)
     pool.shutdown()
     return n_rows
 

@@ -75,6 +75,11 @@ def main():
                 for l, p, d in itertools.product((0, 1), (0, 1), (1, 4))]
     else:
         grid = [dict(pdl_late=0, prio_split=0, depth=1, sm_reserve=0, decode_ctas=0)]
+        for depth in (2, 3, 4):
+            grid.append(dict(pdl_late=0, prio_split=0, depth=depth, sm_reserve=0, decode_ctas=0))
+        for ctas, reserve in ((32, 0), (64, 0), (48, 32), (64, 32), (96, 0)):   # thinner decode kernels: do the chains of 4 batches overlap?
+            for late in (0, 1):
+                grid.append(dict(pdl_late=late, prio_split=0, depth=4, sm_reserve=reserve, decode_ctas=ctas))
         for reserve in (0, 32):                     # most informative first: the run may be cut short
             for depth in (4, 6, 8):
                 for late, prio in itertools.product((0, 1), (0, 1)):
