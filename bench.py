@@ -161,6 +161,8 @@ def main():
     ap.add_argument('--no-micro', action='store_true')
     ap.add_argument('--pipeline', type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help='batches in flight (2: the encoder of batch i+1 overlaps the decode loop of batch i)')
+    ap.add_argument('--coalesce', type=int, default=1,
+                    help='dynamic batching: this many submitted batches of 64 share one engine launch (one decode chain)')
     ap.add_argument('--ncu-range', action='store_true',
                     help='bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)')
     args = ap.parse_args()
@@ -202,30 +204,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def finish_device(pend):
-        out = pend.result()
-        toks, lps = out['predictions'], out['logprobs']
-        if world > 1:
-            toks, lps = gather_captions(toks, lps, n_total)
-        return toks
-
-    def run_device(k, depth):
-        """k steps; depth 1 = one batch at a time (model(batch)), depth 2 = the next batch is submitted before the
-        previous result is collected, so its encoder overlaps the previous batch's latency-bound decode loop."""
+    def run_device(k, depth, src=None, to_host=False):
+        """k steps; depth 1 = one batch at a time (model(batch)); depth > 1 = up to `depth` engine launches in flight, each
+        serving `coalesce` submitted batches, so the encoder of later batches overlaps the latency-bound decode loops of
+        earlier ones.  src: the step's input (device-resident pixels, or the pinned host tensor for the e2e leg)."""
+        src = img_dev if src is None else src
         pend, toks = [], None
+
+        def collect(p):
+            out = p.result()
+            t, l = out['predictions'], out['logprobs']
+            if to_host:                      # the caller reads the result: D2H inside the timed region
+                t, l = t.cpu(), l.cpu()
+                if world > 1:
+                    t, l = t.to(dev), l.to(dev)
+            if world > 1:
+                t, l = gather_captions(t, l, n_total)
+            return t
         for _ in range(k):
             if depth == 1:     # the reference call: model(batch), one at a time on the caller's stream
-                out = model({'image': img_dev})
+                out = model({'image': src})
                 toks = out['predictions']
                 if world > 1:
                     toks, _ = gather_captions(toks, out['logprobs'], n_total)
                 continue
-            h = model.submit({'image': img_dev}, depth=depth)
-            pend.append(h)
-            if len(pend) >= depth:
-                toks = finish_device(pend.pop(0))
+            pend.append(model.submit({'image': src}, depth=depth, coalesce=args.coalesce))
+            if len(pend) >= depth * args.coalesce:
+                toks = collect(pend.pop(0))
         while pend:
-            toks = finish_device(pend.pop(0))
+            toks = collect(pend.pop(0))
         return toks
 
     # ---------------- device-resident timing (`value`) ----------------
@@ -234,7 +241,7 @@ def main():
         for depth in (1, args.pipeline):
             if depth in results:
                 continue
-            toks = run_device(max(args.warmup, 2 * depth), depth)   # every engine slot past its first (capturing) call
+            toks = run_device(max(args.warmup, 2 * depth * args.coalesce), depth)   # every engine slot past its first (capturing) call
             barrier()
             if depth == args.pipeline:
                 sampler = ClockSampler(local)
@@ -264,50 +271,69 @@ def main():
     value = n_total * args.steps / (ms / 1e3)
     sync_value = n_total * args.steps / (results[1][0] / 1e3)
 
-    # ---------------- end to end through the C ABI with HOST buffers (`e2e`) ----------------
+    # ---------------- end to end with HOST buffers (`e2e`) ----------------
+    # coalesce == 1: through the C ABI (gitb200_generate_host_async / _finish), one engine per batch in flight;
+    # coalesce  > 1: through the Python surface (model.submit on pinned host tensors -> .cpu()), the same dynamic batching
+    #                as the device-resident leg.  Either way every step's H2D pixel copy and D2H token copy is timed.
     sp = model._search_struct()
-    n_e2e_slots = args.pipeline
-    slots = []
-    for k in range(n_e2e_slots):
-        lib, _ = model._ensure_engine(k)
-        slots.append(dict(engine=model._slots[k]['engine'],
-                          stream=stream if k == 0 else torch.cuda.Stream(device=dev),
-                          tok=torch.empty((B, MAX_STEPS), dtype=torch.long).pin_memory(),
-                          lp=torch.empty((B,), dtype=torch.float32).pin_memory(), busy=False))
-    n_out = ctypes.c_int32(0)
+    lib = _lib.load()
+    if args.coalesce > 1:
+        with torch.cuda.stream(stream):
+            run_device(2 * args.pipeline * args.coalesce, args.pipeline, img_host, True)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            toks = run_device(args.steps, args.pipeline, img_host, True)
+            for sl in model._slots:
+                if sl['stream'] is not None:
+                    stream.wait_stream(sl['stream'])
+            e1.record(stream)
+            barrier()
+            ms_e2e = e0.elapsed_time(e1)
+        e2e_api = 'model.submit({image: pinned host tensor}, depth=%d, coalesce=%d) -> result().cpu()' % (args.pipeline, args.coalesce)
+    else:
+        n_e2e_slots = args.pipeline
+        slots = []
+        for k in range(n_e2e_slots):
+            lib, _ = model._ensure_engine(k)
+            slots.append(dict(engine=model._slots[k]['engine'],
+                              stream=stream if k == 0 else torch.cuda.Stream(device=dev),
+                              tok=torch.empty((B, MAX_STEPS), dtype=torch.long).pin_memory(),
+                              lp=torch.empty((B,), dtype=torch.float32).pin_memory(), busy=False))
+        n_out = ctypes.c_int32(0)
 
-    def e2e_finish(sl):
-        _lib.check(lib.gitb200_generate_finish(sl['engine'], ctypes.byref(n_out)), sl['engine'], 'generate_finish')
-        sl['busy'] = False
-        if world > 1:
-            gather_captions(sl['tok'].to(dev, non_blocking=True), sl['lp'].to(dev, non_blocking=True), n_total)
+        def e2e_finish(sl):
+            _lib.check(lib.gitb200_generate_finish(sl['engine'], ctypes.byref(n_out)), sl['engine'], 'generate_finish')
+            sl['busy'] = False
+            if world > 1:
+                gather_captions(sl['tok'].to(dev, non_blocking=True), sl['lp'].to(dev, non_blocking=True), n_total)
 
-    def run_host(k):
-        """k steps through the C ABI with HOST buffers: H2D pixels, generate, D2H tokens; `pipeline` engines in flight."""
-        for i in range(k):
-            sl = slots[i % n_e2e_slots]
-            if sl['busy']:
-                e2e_finish(sl)
-            _lib.check(lib.gitb200_generate_host_async(sl['engine'], img_host.data_ptr(), B, 0, None, 0, ctypes.byref(sp),
-                                                       sl['tok'].data_ptr(), sl['lp'].data_ptr(), sl['stream'].cuda_stream),
-                       sl['engine'], 'generate_host_async')
-            sl['busy'] = True
-        for sl in slots:
-            if sl['busy']:
-                e2e_finish(sl)
+        def run_host(k):
+            """k steps through the C ABI with HOST buffers: H2D pixels, generate, D2H tokens; `pipeline` engines in flight."""
+            for i in range(k):
+                sl = slots[i % n_e2e_slots]
+                if sl['busy']:
+                    e2e_finish(sl)
+                _lib.check(lib.gitb200_generate_host_async(sl['engine'], img_host.data_ptr(), B, 0, None, 0, ctypes.byref(sp),
+                                                           sl['tok'].data_ptr(), sl['lp'].data_ptr(), sl['stream'].cuda_stream),
+                           sl['engine'], 'generate_host_async')
+                sl['busy'] = True
+            for sl in slots:
+                if sl['busy']:
+                    e2e_finish(sl)
 
-    with torch.cuda.stream(stream):
-        run_host(2 * n_e2e_slots)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run_host(args.steps)
-        for sl in slots[1:]:
-            stream.wait_stream(sl['stream'])
-        e1.record(stream)
-        barrier()
-        ms_e2e = e0.elapsed_time(e1)
-        tok_host, lp_host = slots[0]['tok'], slots[0]['lp']
+        with torch.cuda.stream(stream):
+            run_host(2 * n_e2e_slots)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run_host(args.steps)
+            for sl in slots[1:]:
+                stream.wait_stream(sl['stream'])
+            e1.record(stream)
+            barrier()
+            ms_e2e = e0.elapsed_time(e1)
+        e2e_api = 'gitb200_generate_host_async / gitb200_generate_finish (C ABI), %d engines in flight' % n_e2e_slots
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,13 +401,15 @@ def main():
                        'global_batch': n_total, 'per_gpu_batch': B, 'parallelism': 'image-parallel x%d + 1 all_gather' % world,
                        'l2': 'inputs larger than L2: each step streams ~0.3 GB weights + 0.23 GB image K/V + activations (> 126 MB)',
                        'compute': 'bf16 operands, fp32 accumulate, fp32 residual stream',
-                       'pipeline': '%d batches of 64 in flight (one engine + stream each: encoder / prefill of later batches overlap the '
-                                   'latency-bound decode loops of earlier ones; every step does all of its work inside the timed '
-                                   'region; sync_value = one batch at a time through model(batch))' % args.pipeline
+                       'pipeline': ('%d engine launches in flight x %d submitted batches of %d per launch (model.submit: dynamic '
+                                    'batching -- the batches of one launch share one encoder pass and one decode chain; the encoder / '
+                                    'prefill of later launches overlap the latency-bound decode loops of earlier ones; every step does '
+                                    'all of its work inside the timed region; sync_value = one batch of %d at a time through '
+                                    'model(batch))' % (args.pipeline, args.coalesce, B, B))
                        if args.pipeline > 1 else '1 (synchronous model(batch) calls)'},
             'sync_value': sync_value,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
-                    'h2d_bytes_per_step': img_host.numel() * 4, 'd2h_bytes_per_step': tok_host.numel() * 8 + lp_host.numel() * 4},
+                    'h2d_bytes_per_step': img_host.numel() * 4, 'd2h_bytes_per_step': B * MAX_STEPS * 8 + B * 4, 'api': e2e_api},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'roofline': roofline,

@@ -73,6 +73,82 @@ class _Pending(object):
         return self._out
 
 
+def greedy_width(pred, eos):
+    """Number of columns the reference's greedy loop produces for these rows ALONE: it stops right after the first step
+    in which every row holds EOS (layers/decoder.py:316-320); rows that finished earlier are EOS-forced (:347-351), which
+    adds 0 to their logprob and nothing to `num_valid` (:433-438), so extra columns never change a row's result."""
+    all_eos = (pred == eos).all(dim=0)
+    hit = torch.nonzero(all_eos)
+    return int(hit[0]) + 1 if hit.numel() else pred.shape[1]
+
+
+class _Group(object):
+    """Batches submitted one by one that share ONE engine launch (dynamic batching): one encoder pass over all their
+    images and one decode chain over all their rows.  The decode chain is ~45 latency-bound kernels per step whose
+    duration barely depends on the row count, so k batches in one chain cost little more than one."""
+
+    def __init__(self, model, key, depth, want):
+        self.model, self.key, self.depth, self.want = model, key, depth, want
+        self.images, self.rows = [], []
+        self.pending, self.out = None, None
+
+    def add(self, image, rows):
+        self.images.append(image)
+        self.rows.append(rows)
+        return len(self.rows) - 1
+
+    def launch(self):
+        if self.pending is not None or self.out is not None:
+            return
+        m = self.model
+        if m._open_group is self:
+            m._open_group = None
+        first = self.images[0]
+        if len(self.images) == 1:
+            cat = first
+        elif isinstance(first, (list, tuple)):
+            cat = [torch.cat([im[f] for im in self.images], dim=0) for f in range(len(first))]
+        else:
+            cat = torch.cat(self.images, dim=0)
+        self.images = None
+        self.pending = m.submit({'image': cat}, depth=self.depth)
+
+    def result(self):
+        if self.out is None:
+            self.launch()
+            self.out = self.pending.result()
+            self.pending = None
+        return self.out
+
+
+class _Member(object):
+    """Handle of one batch inside a _Group: `.result()` is what `model(batch)` would have returned for it."""
+
+    def __init__(self, group, index):
+        self.group, self.index = group, index
+        self._out = None
+
+    def result(self):
+        if self._out is not None:
+            return self._out
+        g = self.group
+        out = g.result()
+        r0 = sum(g.rows[:self.index])
+        r1 = r0 + g.rows[self.index]
+        pred, lp = out['predictions'][r0:r1], out['logprobs'][r0:r1]
+        m = g.model
+        if isinstance(m.decoder, AutoRegressiveBeamSearch) and pred.shape[1] > 1 and len(g.rows) > 1:
+            if bool((pred[:, 1] == m.eos_index).all()):
+                # this batch alone would have taken the reference's empty-caption exit (layers/decoder.py:279-291)
+                warnings.warn('Empty captions predicted. You may want to increase beam size or ensure your step '
+                              'function is working properly.', RuntimeWarning)
+                pred, lp = pred[:, 1:2], lp.reshape(-1)[:, None]
+            else:
+                pred = pred[:, :greedy_width(pred, m.eos_index)]
+        self._out = {'predictions': pred, 'logprobs': lp}
+        return self._out
+
+
 class _Holder(nn.Module):
     """Attribute container so that parameters get the reference's dotted names."""
 
@@ -140,6 +216,7 @@ class GitB200CaptioningModel(nn.Module):
         self._slots = [dict(engine=None, sig=None, stream=None, pending=None) for _ in range(self.n_slots)]
         self._engine_device = None
         self._next_slot = 0
+        self._open_group = None      # batches waiting to be launched together (submit(..., coalesce=k))
 
     # ---------------------------------------------------------------- engine plumbing
     def _device(self):
@@ -236,14 +313,14 @@ class GitB200CaptioningModel(nn.Module):
         dev = self._device()
         if isinstance(image, (list, tuple)):
             frames = len(image)
-            ims = [im.to(device=dev, dtype=torch.float32) for im in image]
+            ims = [im.to(device=dev, dtype=torch.float32, non_blocking=True) for im in image]
             B = ims[0].shape[0]
             if any(im.shape != ims[0].shape for im in ims):
                 raise ValueError('all frames of a batch must share one size')
             x = ims[0].contiguous() if frames == 1 else torch.stack(ims, dim=0).contiguous()
         else:
             frames = 0
-            x = image.to(device=dev, dtype=torch.float32).contiguous()
+            x = image.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
             B = x.shape[0]
         if x.dim() != (4 if frames <= 1 else 5) or x.shape[-3] != 3:
             raise ValueError('images must be [B, 3, H, W] tensors (got %s)' % (tuple(x.shape),))
@@ -263,15 +340,25 @@ class GitB200CaptioningModel(nn.Module):
         return self.submit(batch, forced_tokens, return_step_logits, slot=0, _caller_stream=True).result()
 
     @torch.no_grad()
-    def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None, depth=2, _caller_stream=False):
+    def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None, depth=2, _caller_stream=False,
+               coalesce=1):
         """Enqueue `model(batch)` without waiting: returns a handle whose `.result()` gives the reference's output
-        dict.  Successive submits rotate over `depth` engines / streams (each engine: one call in flight)."""
+        dict.  Successive submits rotate over `depth` engines / streams (each engine: one call in flight).
+
+        coalesce = k > 1 (dynamic batching): k successive batches of one shape are launched as ONE engine call -- one
+        encoder pass, one decode chain over all their rows -- as soon as the k-th arrives or a result is asked for; every
+        handle still returns exactly its own batch's reference output (greedy width and empty-caption exit included)."""
         if self.training:
             raise NotImplementedError('training (loss / SCST branches) is out of scope: call model.eval()')
         if 'image' not in batch:
             raise NotImplementedError("batch without 'image' is not supported")
         if 'context' in batch:
             raise NotImplementedError("'context' batches are not produced by the reference inference path")
+        if (int(coalesce) > 1 and slot is None and not _caller_stream and forced_tokens is None and not return_step_logits
+                and 'prefix' not in batch):
+            return self._submit_coalesced(batch['image'], depth, int(coalesce))
+        if self._open_group is not None:
+            self._open_group.launch()         # keep the submission order
         if slot is None:
             depth = max(1, min(int(depth), self.n_slots))
             slot = self._next_slot % depth
@@ -283,6 +370,7 @@ class GitB200CaptioningModel(nn.Module):
         eng = sl['engine']
         dev = self._device()
         cur = torch.cuda.current_stream(dev)
+        x, B, frames = self._pack_images(batch['image'])      # (copies / casts, if any, run on the caller's stream)
         if _caller_stream:
             stream = cur                      # synchronous path: the caller's stream (stream 0 -> engine-owned stream)
         else:
@@ -292,7 +380,6 @@ class GitB200CaptioningModel(nn.Module):
                 sl['stream'] = torch.cuda.Stream(device=dev)
             stream = sl['stream']
             stream.wait_stream(cur)           # inputs produced on the caller's stream
-        x, B, frames = self._pack_images(batch['image'])
         sp = self._search_struct()
         prefix, P = None, 0
         if 'prefix' in batch:
@@ -325,6 +412,34 @@ class GitB200CaptioningModel(nn.Module):
         pend = _Pending(self, slot, sp, P, tokens, logprobs, step_logits, (x, prefix, forced))
         sl['pending'] = pend
         return pend
+
+    def _submit_coalesced(self, image, depth, want):
+        dev = self._device()
+        if dev.type != 'cuda':
+            raise RuntimeError('the gitb200 engine runs on CUDA devices only (sm_100a); call model.cuda() first. '
+                               'There is no CPU path.')
+
+        def to_dev(t):
+            return t.to(device=dev, dtype=torch.float32, non_blocking=True)
+        if isinstance(image, (list, tuple)):
+            image = [to_dev(im) for im in image]
+            key = ('list', len(image)) + tuple(tuple(im.shape[1:]) for im in image)
+            rows = image[0].shape[0]
+        else:
+            image = to_dev(image)
+            key = ('tensor',) + tuple(image.shape[1:])
+            rows = image.shape[0]
+        key = key + (id(self.decoder), depth, want)
+        g = self._open_group
+        if g is not None and g.key != key:
+            g.launch()
+            g = None
+        if g is None:
+            g = self._open_group = _Group(self, key, depth, want)
+        member = _Member(g, g.add(image, rows))
+        if len(g.rows) >= want:
+            g.launch()
+        return member
 
     def _finish(self, pend):
         lib = _lib.load()

@@ -323,3 +323,37 @@ def test_engine_slots_share_one_weight_copy_and_scheduling_switches():
     finally:
         m.set_engine_option('pdl_late', 0)
         m.set_engine_option('prio_split', 0)
+
+
+def test_coalesced_submit_matches_sync_calls():
+    """Dynamic batching: batches submitted one by one with coalesce=k share one engine launch (one decode chain over
+    all their rows); every handle must return its own batch's result -- shapes as the reference's per-batch loop would
+    give them, captions equal to one-at-a-time calls up to run-to-run noise."""
+    g = load_golden('base_greedy')
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    from generativeimage2text_b200.synthetic import synthetic_images
+    m = _model(meta, sd, max_steps=12)
+    imgs = [synthetic_images(2 + (i % 2), 0, 900 + i).cuda() for i in range(5)]     # batches of 2 and 3 rows
+    sync = [m({'image': x}) for x in imgs]
+    launches0 = m.launch_count()
+    pend = [m.submit({'image': x}, depth=2, coalesce=3) for x in imgs]      # groups: [0,1,2] launched, [3,4] still open
+    assert m._open_group is not None and len(m._open_group.rows) == 2
+    outs = [p.result() for p in pend]                                       # asking for a result launches the open group
+    assert m._open_group is None
+    for a, b, x in zip(sync, outs, imgs):
+        assert b['predictions'].shape[0] == x.shape[0]
+        _same_captions(a, b)
+    assert m.launch_count() > launches0
+    # a list input (video frames) coalesces frame by frame; a prefix or a parity hook is never coalesced
+    vg = load_golden('vatex_greedy')
+    vsd, vbatch = golden_inputs(vg['meta'])
+    vm = _model(vg['meta'], vsd, max_steps=8)
+    frames_a = [f.cuda() for f in vbatch['image']]
+    frames_b = [f.flip(-1).contiguous() for f in frames_a]
+    ra, rb = vm({'image': frames_a}), vm({'image': frames_b})
+    pa, pb = vm.submit({'image': frames_a}, coalesce=2), vm.submit({'image': frames_b}, coalesce=2)
+    _same_captions(ra, pa.result())
+    _same_captions(rb, pb.result())
+    h = m.submit({'image': imgs[0][:1], 'prefix': torch.tensor([[101, 2054]]).cuda()}, coalesce=4)
+    assert h.result()['predictions'].shape[0] == 1 and m._open_group is None
