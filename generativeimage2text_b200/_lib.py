@@ -60,6 +60,7 @@ SIGNATURES = {
     'gitb200_preproc_destroy': (None, [c_void_p]),
     'gitb200_preproc_last_error': (c_char_p, [c_void_p]),
     'gitb200_preproc_launch_count': (c_int64, [c_void_p]),
+    'gitb200_preproc_set_option': (c_int, [c_void_p, c_char_p, c_int64]),
     'gitb200_preproc_run': (c_int, [c_void_p, c_void_p, c_int64, c_int, ctypes.POINTER(ImageDesc), c_int,
                                     ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_int64, c_void_p]),
     'gitb200_preproc_coeffs': (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_void_p, c_void_p, c_int]),

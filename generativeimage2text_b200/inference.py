@@ -111,8 +111,9 @@ class ImageTransform(object):
     """`get_image_transform(param)`: callable on one decoded image like the reference's `Compose`, but the result is a
     CUDA tensor (the reference's callers do `.cuda()` next, a no-op then); `batch()` transforms many images per call."""
 
-    def __init__(self, param, device=None):
+    def __init__(self, param, device=None, fast=None):
         param = param or {}
+        self.fast = bool(int(os.environ.get('GITB200_PREPROC_FAST', '0'))) if fast is None else bool(fast)
         self.crop_size = param.get('test_crop_size', 224)
         self.respect_ratio_max = param.get('test_respect_ratio_max')
         self.minmax = MinMaxResizeForTest(self.crop_size, self.respect_ratio_max) if self.respect_ratio_max else None
@@ -149,6 +150,7 @@ class ImageTransform(object):
             if lib.gitb200_preproc_create(self.device.index or 0, ctypes.byref(h)) != 0:
                 raise RuntimeError('gitb200_preproc_create failed: %s' % (lib.gitb200_preproc_last_error(None) or b'').decode())
             self._handle = h
+            lib.gitb200_preproc_set_option(h, b'fast', int(self.fast))
         return _lib.load()
 
     def batch(self, imgs):
@@ -206,9 +208,9 @@ class ImageTransform(object):
             pass
 
 
-def get_image_transform(param, device=None):
+def get_image_transform(param, device=None, fast=None):
     """reference inference.py:111-132."""
-    return ImageTransform(param, device)
+    return ImageTransform(param, device, fast)
 
 
 def _default_tokenizer():

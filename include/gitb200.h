@@ -191,6 +191,8 @@ int gitb200_preproc_create(int device, gitb200_preproc** out);
 void gitb200_preproc_destroy(gitb200_preproc* p);
 const char* gitb200_preproc_last_error(const gitb200_preproc* p);
 int64_t gitb200_preproc_launch_count(const gitb200_preproc* p);
+/* Switches: "fast" (0/1) -- word-load kernels (same results) where their alignment preconditions hold. */
+int gitb200_preproc_set_option(gitb200_preproc* p, const char* name, int64_t value);
 /* src: packed uint8 RGB images, on the device (src_on_host == 0) or in host memory (pinned or pageable; copied to the
  * device on `stream` first).  mean3 / std3: host float[3].  Work is enqueued on `stream`; a second call on the same
  * handle first waits (on the host) for the previous call's kernels, so use one handle per stream to overlap calls. */
