@@ -1,10 +1,15 @@
 """bench.py -- captions/sec of the GIT captioning hot path (BASELINE.json metric).
 
-A "step" is one `model({'image': x})` call over one batch of synthetic 224x224 images: CLIP-ViT encoder ->
+A "step" is one batch of 64 synthetic 224x224 images captioned through the reference surface: CLIP-ViT encoder ->
 visual projection -> image-row prefill of the 6 decoder layers -> 39 KV-cached greedy decode steps
 (max_len 40), i.e. the reference's `CaptioningModel.forward` in eval mode with its greedy decoder
 (reference model.py:27-33).  N=1 workload = BASELINE.json configs[1]: GIT_BASE, batch 64, one B200.
 Random-init weights of that architecture (reference initialiser distributions) and synthetic pixels.
+
+Three numbers per run: `sync_value` = `model(batch)` one batch at a time (the reference's calling pattern);
+`value` = the same batches handed to `model.submit(batch, depth, coalesce)` (device-resident pixels): `coalesce` batches
+share one engine launch, `depth` launches are in flight; `e2e` = the same with pinned HOST tensors in and tokens read back.
+Every batch's full work (encoder, prefill, 39 decode steps, search) is inside the timed region in all three.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -153,16 +158,18 @@ def main():
     faulthandler.dump_traceback_later(int(os.environ.get('GITB200_BENCH_WATCHDOG_S', '240')), exit=True)   # a hung run reports where
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=16)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='gitb200')
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true')
-    ap.add_argument('--pipeline', type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 7, 8],
-                    help='batches in flight (2: the encoder of batch i+1 overlaps the decode loop of batch i)')
-    ap.add_argument('--coalesce', type=int, default=1,
-                    help='dynamic batching: this many submitted batches of 64 share one engine launch (one decode chain)')
+    ap.add_argument('--pipeline', type=int, default=2, choices=[1, 2, 3, 4, 5, 6, 7, 8],
+                    help='engine launches in flight (the encoder of launch i+1 overlaps the decode loop of launch i)')
+    ap.add_argument('--coalesce', type=int, default=4, choices=[1, 2, 3, 4],
+                    help='dynamic batching: this many submitted batches of 64 share one engine launch (one decode chain over '
+                         'all their rows). Measured on B200 (tools/batch_sweep.py, profiles/batch_sweep_r01.txt): 64 x 4 in '
+                         'flight 5319 captions/s, 128 x 3 6086, 256 x 2 6353, 256 x 3 6432')
     ap.add_argument('--ncu-range', action='store_true',
                     help='bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)')
     args = ap.parse_args()
@@ -171,6 +178,7 @@ def main():
         run_reference_arm(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    args.coalesce = max(1, min(args.coalesce, 256 // max(1, args.batch)))    # one decode chain serves at most 256 rows
 
     import ctypes
     import torch
@@ -242,6 +250,14 @@ def main():
             if depth in results:
                 continue
             toks = run_device(max(args.warmup, 2 * depth * args.coalesce), depth)   # every engine slot past its first (capturing) call
+            tail = args.steps % args.coalesce
+            if depth > 1 and args.coalesce > 1 and tail:
+                # the last launch of the timed region serves only `tail` batches: let every slot capture the decode-step
+                # graph of that row count too (warm-up, like the full-size launches above)
+                small = torch.cat([img_dev] * tail, dim=0)
+                for k in range(depth):
+                    model.submit({'image': small}, slot=k).result()
+                del small
             barrier()
             if depth == args.pipeline:
                 sampler = ClockSampler(local)
@@ -386,9 +402,9 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        v, sec, threads = cpu_baseline_run(4, 1, 0)
+        v, sec, threads = cpu_baseline_run(8, 1, 0)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': 'one batch of 4 images through oracle/git_oracle.py in as-shipped mode (no KV cache, fp32, %.1f s); '
+               'sample': 'one batch of 8 images through oracle/git_oracle.py in as-shipped mode (no KV cache, fp32, %.1f s); '
                          'same per-image work as the batch-64 workload' % sec}
 
     if rank == 0:

@@ -156,9 +156,11 @@ struct gitb200_engine {
   std::map<TmapKey, CUtensorMap> tmaps;
 
   // decode-step graph cache
-  cudaGraphExec_t step_graph = nullptr;
-  std::vector<long long> step_graph_key;
-  int64_t launches_per_step = 0;
+  // (a call's graph is keyed by its row count, cache geometry and buffer addresses; several shapes alternate when batches
+  //  are coalesced into launches of different sizes, so a handful of instantiated graphs are kept)
+  struct StepGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; unsigned long long last_use = 0; };
+  std::map<std::vector<long long>, StepGraph> step_graphs;
+  unsigned long long step_graph_clock = 0;
   int last_gemm_grid = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t own_event = nullptr;
@@ -186,6 +188,11 @@ struct Lane {
   int chain_idx = 0;        // out: chain position / CTAs of the last kernel launched by step_layers
   unsigned int chain_ctas = 0;
 };
+
+static void drop_step_graphs(gitb200_engine* h) {
+  for (auto& kv : h->step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->step_graphs.clear();
+}
 
 static int fail(gitb200_engine* h, const char* fmt, ...) {
   char buf[1024];
@@ -574,7 +581,7 @@ extern "C" int64_t gitb200_launch_count(const gitb200_engine* h) { return h ? h-
 extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value) {
   if (!h || !name) return 1;
   // the captured decode-step graph bakes the launch configuration in: drop it whenever an option changes
-  if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; h->step_graph_key.clear(); }
+  drop_step_graphs(h);
   if (strcmp(name, "pdl_late") == 0) {   // process-wide (a __constant__ the chain kernels read)
     const int v = value != 0 ? 1 : 0;
     cudaSetDevice(h->device);
@@ -689,7 +696,7 @@ extern "C" int gitb200_share_weights(gitb200_engine* h, gitb200_engine* src) {
   std::vector<DevBuf*> dst = weight_bufs(h), from = weight_bufs(src);
   for (size_t i = 0; i < dst.size(); ++i) dst[i]->borrow(*from[i]);
   h->tmaps.clear();
-  if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; h->step_graph_key.clear(); }
+  drop_step_graphs(h);
   h->seen = src->seen;
   h->finalized = true;
   h->weights_from = src;
@@ -700,7 +707,7 @@ extern "C" void gitb200_destroy(gitb200_engine* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  drop_step_graphs(h);
   for (int i = 0; i < kMaxLanes; ++i) { if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->host_state) cudaFreeHost(h->host_state);
