@@ -155,7 +155,7 @@ def run_reference_arm(args, rank, world):
 
 def main():
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get('GITB200_BENCH_WATCHDOG_S', '240')), exit=True)   # a hung run reports where
+    faulthandler.dump_traceback_later(int(os.environ.get('GITB200_BENCH_WATCHDOG_S', '480')), exit=True)   # a hung run reports where
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=16)

@@ -1,4 +1,6 @@
-"""Per-kernel (start, dependency satisfied, end) stamps of block 0 inside the replayed decode-step graph."""
+"""Per-kernel (start, dependency satisfied, end) stamps of block 0 inside the replayed decode-step graph.
+
+    [ROWS=256] python tools/step_timeline2.py      (ROWS = images per engine launch, default 64)"""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +13,7 @@ m = get_git_model(Tok(), {})
 m.load_state_dict(synthetic_state_dict({}, 0, 'init'))
 m = m.cuda().eval()
 m.decoder = AutoRegressiveBeamSearch(102, max_steps=40, beam_size=1, per_node_beam_size=1, fix_missing_prefix=True)
-img = synthetic_images(64).cuda()
+img = synthetic_images(int(os.environ.get('ROWS', '64'))).cuda()
 s = torch.cuda.Stream()
 lib = _lib.load()
 NAMES = {2: 'layernorm', 3: 'decode_attn', 4: 'embed_ln', 5: 'greedy_select'}
