@@ -231,9 +231,15 @@ __device__ __forceinline__ void dec_attn_update(float (&sc)[4], const uint4 (&w)
 // of this kernel's HBM stream overlaps the QKV GEMM that precedes it, and later fetches overlap the arithmetic of
 // the previous item.  128 threads = 16 key groups x 8 lanes (8 head dims each, 128-bit accesses); scores are folded
 // into per-group online-softmax states merged at the end (flash-decoding style), single pass over K and V.
-template <int NQ>
+//
+// kPipe (NQ == 1 only): software pipelining of the two global-memory round trips an item used to expose -- the step's own
+// q/k/v of item k+1 are requested at the top of item k, and the text K/V rows of an item are requested before its
+// image-key loop (shared memory) and consumed after it.  At 256 rows a CTA walks ~10 items, so the exposed latencies
+// (not the HBM stream) bounded the kernel: 58 us for 158 MB.
+template <int NQ, bool kPipe = false>
 __global__ void __launch_bounds__(128)
 decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const DecAttnParams p) {
+  constexpr bool kPipeOn = kPipe && NQ == 1;
   extern __shared__ uint8_t attn_dyn[];
   uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_dyn) + 127) & ~uintptr_t(127));
   const size_t kv_bytes = static_cast<size_t>(p.chunk_rows) * 128;  // one of K / V of one unit
@@ -325,9 +331,32 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     }
   }
 
+  // kPipe: (q, k | v) of the NEXT item, requested one item ahead
+  float nxt_a = 0.f, nxt_b = 0.f;
+  auto request_qkv = [&](int k, float& a, float& b2) {
+    if (k < n_my) {
+      const int item = blockIdx.x + k * G;
+      const int b = item / H, h = item - b * H;
+      const float* row = p.qkv + static_cast<long long>(b) * 3 * D + h * 64;
+      if (tid < 64) {
+        a = __ldcg(row + tid);
+        b2 = __ldcg(row + D + tid);
+      } else {
+        a = __ldcg(row + 2 * D + tid - 64);
+      }
+    }
+  };
+  if (kPipeOn) request_qkv(kPre, nxt_a, nxt_b);   // items 0..kPre-1 were requested above
+
   for (int k = 0; k < n_my; ++k) {
     const int item = blockIdx.x + k * G;
     const int b = item / H, h = item - b * H;
+    float cur_a = 0.f, cur_b = 0.f;
+    if (kPipeOn && k >= kPre) {
+      cur_a = nxt_a;
+      cur_b = nxt_b;
+      request_qkv(k + 1, nxt_a, nxt_b);
+    }
     // ---- q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V (bf16) ----
     for (int qi = 0; qi < NQ; ++qi) {
       const int r = b * NQ + qi;
@@ -336,8 +365,8 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       const bool have = (NQ == 1) && (k < kPre);
       const bool acc_mode = p.bqkv != nullptr;
       if (tid < 64) {
-        const float qv = have ? pre_a[k < kPre ? k : 0] : __ldcg(row + tid);
-        const float kv = have ? pre_b[k < kPre ? k : 0] : __ldcg(row + D + tid);
+        const float qv = have ? pre_a[k < kPre ? k : 0] : (kPipeOn ? cur_a : __ldcg(row + tid));
+        const float kv = have ? pre_b[k < kPre ? k : 0] : (kPipeOn ? cur_b : __ldcg(row + D + tid));
         q_s[qi][tid] = (qv + (acc_mode ? bias[tid] : 0.f)) * 0.125f;
         p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(kv + (acc_mode ? bias[D + tid] : 0.f));
         if (acc_mode) {
@@ -346,7 +375,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         }
       } else {
         const int d = tid - 64;
-        const float vv = have ? pre_a[k < kPre ? k : 0] : __ldcg(row + 2 * D + d);
+        const float vv = have ? pre_a[k < kPre ? k : 0] : (kPipeOn ? cur_a : __ldcg(row + 2 * D + d));
         p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(vv + (acc_mode ? bias[2 * D + d] : 0.f));
         if (acc_mode) row[2 * D + d] = 0.f;
       }
@@ -366,38 +395,49 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       }
     }
     // ---- text keys (global loads): each beam row has its own history (through the src_row indirection) ----
+    auto text_chunk_load = [&](int r, int base, uint4 (&u)[4], uint4 (&w)[4]) {
 #pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) {
-      const int r = b * NQ + qi;
-      for (int base = 0; base < n_txt; base += 64) {
-        uint4 u[4], w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int j = base + grp + 16 * i;
-          if (j < n_txt) {
-            const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
-            const long long off = (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8;
-            u[i] = *reinterpret_cast<const uint4*>(p.txt_k + off);
-            w[i] = *reinterpret_cast<const uint4*>(p.txt_v + off);
-          } else {
-            u[i] = make_uint4(0, 0, 0, 0);
-            w[i] = make_uint4(0, 0, 0, 0);
-          }
+      for (int i = 0; i < 4; ++i) {
+        const int j = base + grp + 16 * i;
+        if (j < n_txt) {
+          const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + j] : r;
+          const long long off = (static_cast<long long>(pr) * p.T_alloc + j) * D + h * 64 + gl * 8;
+          u[i] = *reinterpret_cast<const uint4*>(p.txt_k + off);
+          w[i] = *reinterpret_cast<const uint4*>(p.txt_v + off);
+        } else {
+          u[i] = make_uint4(0, 0, 0, 0);
+          w[i] = make_uint4(0, 0, 0, 0);
         }
-        float sc[4];
+      }
+    };
+    auto text_chunk_use = [&](int qi, int base, const uint4 (&u)[4], const uint4 (&w)[4]) {
+      float sc[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float kf[8];
-          bf16x8_to_f32(u[i], kf);
-          float a = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        float kf[8];
+        bf16x8_to_f32(u[i], kf);
+        float a = 0.f;
 #pragma unroll
-          for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[d], a);
-          a += __shfl_xor_sync(0xffffffffu, a, 1);
-          a += __shfl_xor_sync(0xffffffffu, a, 2);
-          a += __shfl_xor_sync(0xffffffffu, a, 4);
-          sc[i] = (base + grp + 16 * i < n_txt) ? a : -INFINITY;
+        for (int d = 0; d < 8; ++d) a = fmaf(qreg[qi][d], kf[d], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        sc[i] = (base + grp + 16 * i < n_txt) ? a : -INFINITY;
+      }
+      dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
+    };
+    uint4 tu[4], tw[4];                       // kPipe: text positions 0..63 of this item, in flight across the image loop
+    if (kPipeOn) {
+      text_chunk_load(b, 0, tu, tw);
+    } else {
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+        const int r = b * NQ + qi;
+        for (int base = 0; base < n_txt; base += 64) {
+          uint4 u[4], w[4];
+          text_chunk_load(r, base, u, w);
+          text_chunk_use(qi, base, u, w);
         }
-        dec_attn_update(sc, w, m_run[qi], l_run[qi], acc[qi]);
       }
     }
     // ---- image keys from shared memory: shared by the NQ beams of this image ----
@@ -437,6 +477,14 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       }
       __syncthreads();  // everyone is done with this buffer: refill it with the unit after next
       if (tid == 0 && u_idx + 2 < n_units) issue_unit(u_idx + 2);
+    }
+    if (kPipeOn) {
+      text_chunk_use(0, 0, tu, tw);
+      for (int base = 64; base < n_txt; base += 64) {   // captions longer than 64 tokens: the rest the plain way
+        uint4 u[4], w[4];
+        text_chunk_load(b, base, u, w);
+        text_chunk_use(0, base, u, w);
+      }
     }
     // ---- merge the 16 group states: 4 groups of a warp by shuffles, the 4 warps through smem ----
 #pragma unroll

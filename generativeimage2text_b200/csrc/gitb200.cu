@@ -118,6 +118,7 @@ struct gitb200_engine {
   bool epi_direct = false; // measured: the staged transpose is faster on every ViT shape (direct stores are LSU bound)
   // (kept switchable)   // normal-mode GEMM epilogue: registers -> global (true) or staged smem transpose (false)
   bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
+  bool attn_pipe = true;  // decode attention with software-pipelined q/k/v and text K/V requests (attention.cuh kPipe)
   bool prio_split = false; // decode loop on an engine-owned HIGH-priority stream (encoder / prefill stay on the caller's):
                           // with several batches in flight the short decode kernels are dispatched ahead of the waves of
                           // another batch's encoder kernels
@@ -589,6 +590,7 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
     return 0;
   }
   if (strcmp(name, "prio_split") == 0) { h->prio_split = value != 0; return 0; }
+  if (strcmp(name, "attn_pipe") == 0) { h->attn_pipe = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
@@ -1121,7 +1123,8 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
     TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
     TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
     dim3 grid(std::min(h->decode_ctas > 0 ? std::min(h->attn_grid, h->decode_ctas) : h->attn_grid, ln_.nb * h->cfg.dec_heads));
-    if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+    if (beam == 1 && h->attn_pipe) CK(launch_k(pdl, decode_attn_kernel<1, true>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+    else if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
     CKL(h, "decode_attn_kernel");
@@ -1156,6 +1159,7 @@ static int set_attn_smem_limit(gitb200_engine* h) {
   const int items = h->cur_B * h->cfg.dec_heads;
   h->attn_grid = std::min(items, per_sm * h->num_sms);
   CK(cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
+  CK(cudaFuncSetAttribute(decode_attn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(h->chain.ensure(256 * kMaxLanes));
   CK(cudaMemset(h->chain.p, 0, 256 * kMaxLanes));
