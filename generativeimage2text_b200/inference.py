@@ -75,22 +75,17 @@ class MinMaxResizeForTest(object):
         self.max_size = max_size
 
     def get_size(self, image_size):
+        """(width, height) of the decoded image -> (out_h, out_w)."""
         w, h = image_size
-        size = self.min_size
-        max_size = self.max_size
-        min_original_size = float(min((w, h)))
-        max_original_size = float(max((w, h)))
-        if max_original_size / min_original_size * size > max_size:
-            size = int(round(max_size * min_original_size / max_original_size))
-        if (w <= h and w == size) or (h <= w and h == size):
+        short, long_ = float(min(w, h)), float(max(w, h))
+        target = self.min_size
+        if long_ / short * target > self.max_size:            # the longer edge would overshoot: shrink the target
+            target = int(round(self.max_size * short / long_))
+        if min(w, h) == target:                               # already there: no resampling at all
             return (h, w)
         if w < h:
-            ow = size
-            oh = int(size * h / w)
-        else:
-            oh = size
-            ow = int(size * w / h)
-        return (oh, ow)
+            return (int(target * h / w), target)
+        return (target, int(target * w / h))
 
     def __repr__(self):
         return 'MinMaxResizeForTest({}, {})'.format(self.min_size, self.max_size)
