@@ -9,7 +9,6 @@ token ids come out of libgitb200.so (hand-written sm_100a kernels).  PyTorch onl
 storage, the CUDA stream and the output tensors.
 """
 import ctypes
-import math
 import warnings
 
 import torch

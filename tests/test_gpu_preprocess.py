@@ -3,7 +3,6 @@ oracle, BIT-EXACT (integer / byte work + IEEE fp32 division), and the batched TS
 import base64
 import io
 import json
-import os
 
 import numpy as np
 import pytest

@@ -4,7 +4,6 @@ executing here -- bit for bit; and against the reference's own `get_image_transf
 /root/reference is present."""
 import numpy as np
 import pytest
-import torch
 
 import preprocess_oracle as po
 import ref_shim

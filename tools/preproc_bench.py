@@ -4,7 +4,6 @@ call = source rows the crop needs (uint8) + fp32 output planes; the uint8 interm
 
     python tools/preproc_bench.py > gpurun_out/preproc_bench.json
 """
-import ctypes
 import json
 import os
 import sys
