@@ -194,6 +194,8 @@ struct DecAttnParams {
   int pos_fixed;
   int chunk_rows;                  // image keys staged per TMA round (<= 512), box_rows * n_boxes
   int box_rows;                    // rows per TMA box (<= 256)
+  int head_major;                  // image K/V cache layout: 0 = [B][M][D] (128-byte slices at a D*2-byte pitch),
+                                   //                         1 = [B][H][M][64] (one (image, head) slice is contiguous)
   ChainSync chain;
 };
 
@@ -278,9 +280,10 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     const int nb = (rows_c + p.box_rows - 1) / p.box_rows;
     mbar_arrive_expect_tx(&bars[u & 1], static_cast<uint32_t>(2 * nb * p.box_rows * 128));
     for (int i = 0; i < nb; ++i) {
-      const int grow = b * p.M + c * p.chunk_rows + i * p.box_rows;
-      tma_load_2d(sK + static_cast<size_t>(i) * p.box_rows * 128, &tmK, &bars[u & 1], h * 64, grow);
-      tma_load_2d(sV + static_cast<size_t>(i) * p.box_rows * 128, &tmV, &bars[u & 1], h * 64, grow);
+      const int grow = (p.head_major ? (b * H + h) * p.M : b * p.M) + c * p.chunk_rows + i * p.box_rows;
+      const int gcol = p.head_major ? 0 : h * 64;
+      tma_load_2d(sK + static_cast<size_t>(i) * p.box_rows * 128, &tmK, &bars[u & 1], gcol, grow);
+      tma_load_2d(sV + static_cast<size_t>(i) * p.box_rows * 128, &tmV, &bars[u & 1], gcol, grow);
     }
   };
   if (tid == 0) {
@@ -528,6 +531,25 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   }
   tl_mark(200003);
   chain_signal(p.chain);
+}
+
+// Image K/V cache [n][B][M][D] (n = layers x {K, V}; what the prefill GEMM epilogue writes) -> [n][B][H][M][64]: the slice
+// one decode-attention item streams becomes one contiguous M x 128-byte run instead of M 128-byte pieces at a D*2-byte
+// pitch. One thread per 16 bytes; once per generate call (the cache is read 39 x 6 times afterwards).
+__global__ void __launch_bounds__(256)
+kv_head_major_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n_img, int M, int H) {
+  const long long per_img = static_cast<long long>(M) * H * 8;      // 16-byte units per image
+  const long long total = n_img * per_img;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long img = i / per_img;
+    const long long r = i - img * per_img;
+    const int m = static_cast<int>(r / (H * 8));
+    const int c = static_cast<int>(r - static_cast<long long>(m) * (H * 8));
+    const int hh = c >> 3, l8 = c & 7;
+    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+    reinterpret_cast<uint4*>(dst)[img * per_img + (static_cast<long long>(hh) * M + m) * 8 + l8] = v;
+  }
 }
 
 }  // namespace gitb200

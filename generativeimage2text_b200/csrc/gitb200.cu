@@ -118,6 +118,8 @@ struct gitb200_engine {
   bool epi_direct = false; // measured: the staged transpose is faster on every ViT shape (direct stores are LSU bound)
   // (kept switchable)   // normal-mode GEMM epilogue: registers -> global (true) or staged smem transpose (false)
   bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
+  bool kv_head_major = false;   // decode attention reads a head-major copy of the image K/V cache (contiguous slices);
+                                // built blind at the end of round 1 (no GPU budget left): off until measured
   bool attn_pipe = true;  // decode attention with software-pipelined q/k/v and text K/V requests (attention.cuh kPipe)
   bool prio_split = false; // decode loop on an engine-owned HIGH-priority stream (encoder / prefill stay on the caller's):
                           // with several batches in flight the short decode kernels are dispatched ahead of the waves of
@@ -143,7 +145,7 @@ struct gitb200_engine {
   // workspaces
   DevBuf x, h, qkv, ctx, u, feats, feats_f32, pos_interp;   // encoder
   DevBuf pt, pxd, phd, pq, pctx, pu;                        // prefill
-  DevBuf img_kv, txt_kv, src_row[2];                        // caches
+  DevBuf img_kv, img_kv_hm, txt_kv, src_row[2];             // caches (img_kv_hm: head-major copy, option kv_head_major)
   DevBuf xd_t, hd_t, qkv_t, ctx_t, t_t, u_t, logits;        // decode step
   DevBuf state, next_token, logprob_sum, tokens_i64, stage_img, stage_tok, stage_lp, prefix_dev;
   DevBuf beam_ws;                                           // beam-search bookkeeping (search.cuh)
@@ -591,6 +593,7 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   }
   if (strcmp(name, "prio_split") == 0) { h->prio_split = value != 0; return 0; }
   if (strcmp(name, "attn_pipe") == 0) { h->attn_pipe = value != 0; return 0; }
+  if (strcmp(name, "kv_head_major") == 0) { h->kv_head_major = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
@@ -660,7 +663,7 @@ static void release_all(gitb200_engine* h) {
   DevBuf* bufs[] = {&h->w_patch, &h->cls, &h->pos_emb, &h->lnpre_g, &h->lnpre_b, &h->lnpost_g, &h->lnpost_b, &h->w_vp,
                     &h->b_vp, &h->lnvp_g, &h->lnvp_b, &h->words_f32, &h->words_bf16, &h->positions, &h->lnemb_g,
                     &h->lnemb_b, &h->out_bias, &h->temb, &h->x, &h->h, &h->qkv, &h->ctx, &h->u, &h->feats, &h->feats_f32, &h->pos_interp,
-                    &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->txt_kv, &h->src_row[0],
+                    &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->img_kv_hm, &h->txt_kv, &h->src_row[0],
                     &h->src_row[1], &h->xd_t, &h->hd_t, &h->qkv_t, &h->ctx_t, &h->t_t, &h->u_t, &h->logits, &h->state,
                     &h->next_token, &h->logprob_sum, &h->tokens_i64, &h->stage_img, &h->stage_tok, &h->stage_lp,
                     &h->prefix_dev, &h->beam_ws, &h->sel_ws, &h->chain};
@@ -1043,6 +1046,14 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
     TRY(launch_gemm(h, gemm_plain(u, F, l.w2.as<bf16>(), F, static_cast<int>(rows), D, F, l.b2.as<float>(), ACT_NONE, xd, t, false), st));
     TRY(launch_ln(h, ln_params(t, nullptr, nullptr, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, static_cast<int>(rows)), D, st));
   }
+  if (h->kv_head_major) {
+    const long long n_img = static_cast<long long>(nl) * 2 * B;
+    CK(h->img_kv_hm.ensure(static_cast<size_t>(n_img) * M * D * 2));
+    const long long units = n_img * M * (D / 8);
+    const int grid = static_cast<int>(std::min<long long>((units + 255) / 256, h->num_sms * 32));
+    kv_head_major_kernel<<<grid, 256, 0, st>>>(h->img_kv.as<bf16>(), h->img_kv_hm.as<bf16>(), n_img, M, H);
+    CKL(h, "kv_head_major_kernel");
+  }
   return 0;
 }
 
@@ -1114,14 +1125,26 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
     DecAttnParams ap{};
     ap.qkv = qkv; ap.bqkv = lean ? nullptr : l.bqkv.as<float>();   // lean QKV: bias already added, plain stores (no re-zeroing)
     ap.img_k = img_kv_ptr(h, j, 0) + img_off; ap.img_v = img_kv_ptr(h, j, 1) + img_off;
+    ap.head_major = h->kv_head_major ? 1 : 0;
+    if (h->kv_head_major) {   // same offsets inside the head-major copy (an image still owns M * D elements)
+      const long long delta = h->img_kv_hm.as<bf16>() - h->img_kv.as<bf16>();
+      ap.img_k += delta;
+      ap.img_v += delta;
+    }
     ap.txt_k = txt_kv_ptr(h, j, 0) + txt_off; ap.txt_v = txt_kv_ptr(h, j, 1) + txt_off;
     ap.src_row = src_row; ap.ctx = ctx; ap.B = ln_.nb; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
     ap.state = state;
     ap.chunk_rows = h->attn_chunk_rows; ap.box_rows = h->attn_box_rows;
     ap.chain = cs;
     CUtensorMap tk, tv;
-    TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
-    TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
+    if (h->kv_head_major) {
+      const long long hm_rows = static_cast<long long>(ln_.nb) * h->cfg.dec_heads * h->cur_M;
+      TRY(get_tmap(h, ap.img_k, hm_rows, 64, 64, ap.box_rows, &tk, false));
+      TRY(get_tmap(h, ap.img_v, hm_rows, 64, 64, ap.box_rows, &tv, false));
+    } else {
+      TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
+      TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
+    }
     dim3 grid(std::min(h->decode_ctas > 0 ? std::min(h->attn_grid, h->decode_ctas) : h->attn_grid, ln_.nb * h->cfg.dec_heads));
     if (beam == 1 && h->attn_pipe) CK(launch_k(pdl, decode_attn_kernel<1, true>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));

@@ -245,7 +245,7 @@ class GitB200CaptioningModel(nn.Module):
             sl['engine'], sl['sig'] = h, None
             import os
             for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'epi_direct', 'lanes', 'sm_reserve',
-                        'decode_ctas', 'prio_split', 'pdl_late', 'attn_pipe'):
+                        'decode_ctas', 'prio_split', 'pdl_late', 'attn_pipe', 'kv_head_major'):
                 v = os.environ.get('GITB200_' + opt.upper())      # debugging switches, e.g. GITB200_USE_2CTA=0
                 if v is not None:
                     _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')

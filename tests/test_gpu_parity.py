@@ -357,3 +357,26 @@ def test_coalesced_submit_matches_sync_calls():
     _same_captions(rb, pb.result())
     h = m.submit({'image': imgs[0][:1], 'prefix': torch.tensor([[101, 2054]]).cuda()}, coalesce=4)
     assert h.result()['predictions'].shape[0] == 1 and m._open_group is None
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('GITB200_TEST_EXPERIMENTAL'),
+                    reason='switches written without GPU time left in round 1: run with GITB200_TEST_EXPERIMENTAL=1 before enabling')
+@pytest.mark.parametrize('name', ['base_greedy', 'vatex_greedy', 'large_greedy'])
+def test_experimental_kv_head_major_matches_default_layout(name):
+    """Engine option kv_head_major (decode attention streams a head-major copy of the image K/V cache): same step logits as
+    the default layout under teacher forcing, for one-box (M = 197 / 257) and chunked (M = 1182) slices."""
+    g = load_golden(name)
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    m = _model(meta, sd)
+    a = m(_to_cuda(batch), return_step_logits=True)
+    forced = torch.full((meta['batch'], meta['max_steps']), 102, dtype=torch.long)
+    forced[:, :a['predictions'].shape[1]] = a['predictions'].cpu()
+    za = m(_to_cuda(batch), forced_tokens=forced, return_step_logits=True)['step_logits'].clone()
+    try:
+        m.set_engine_option('kv_head_major', 1)
+        zb = m(_to_cuda(batch), forced_tokens=forced, return_step_logits=True)['step_logits'].clone()
+    finally:
+        m.set_engine_option('kv_head_major', 0)
+    torch.cuda.synchronize()
+    assert (za - zb).abs().max().item() < 0.05
