@@ -402,9 +402,9 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        v, sec, threads = cpu_baseline_run(8, 1, 0)
+        v, sec, threads = cpu_baseline_run(12, 1, 0)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': 'one batch of 8 images through oracle/git_oracle.py in as-shipped mode (no KV cache, fp32, %.1f s); '
+               'sample': 'one batch of 12 images through oracle/git_oracle.py in as-shipped mode (no KV cache, fp32, %.1f s); '
                          'same per-image work as the batch-64 workload' % sec}
 
     if rank == 0:
