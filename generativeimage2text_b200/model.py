@@ -459,6 +459,10 @@ class GitB200CaptioningModel(nn.Module):
                 lp = logprobs
                 if P:
                     pred = pred[:, P:]                              # reference layers/decoder.py:1004-1006
+                if not bool(torch.isfinite(lp).all()):              # reference layers/decoder.py:419-426
+                    warnings.warn('Infinite log probs encountered. Some final captions may not make sense. This can '
+                                  'happen when the beam size is larger than the number of valid (non-zero probability) '
+                                  'transitions that the step function produces.', RuntimeWarning)
         else:
             pred = tokens[:, P:] if P else tokens
             lp = logprobs[:, None]
