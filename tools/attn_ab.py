@@ -1,5 +1,5 @@
-"""A/B of the decode-attention variants (engine option attn_pipe) on whole synchronous calls:
-    python tools/attn_ab.py > gpurun_out/attn_ab.txt"""
+"""A/B of an engine option (default: attn_pipe; e.g. kv_head_major) on whole synchronous calls:
+    python tools/attn_ab.py [option] > gpurun_out/attn_ab.txt"""
 import json
 import os
 import sys
@@ -14,6 +14,7 @@ class Tok:
     cls_token_id, sep_token_id = 101, 102
 
 
+OPTION = sys.argv[1] if len(sys.argv) > 1 else 'attn_pipe'
 m = get_git_model(Tok(), {})
 m.load_state_dict(synthetic_state_dict({}, 0, 'init'))
 m = m.cuda().eval()
@@ -24,7 +25,7 @@ with torch.cuda.stream(s):
     for rows in (256, 64):
         img = synthetic_images(rows).cuda()
         for pipe in (0, 1, 0, 1):
-            m.set_engine_option('attn_pipe', pipe)
+            m.set_engine_option(OPTION, pipe)
             for _ in range(2):
                 out = m({'image': img})
             torch.cuda.synchronize()
@@ -40,5 +41,5 @@ with torch.cuda.stream(s):
             if key not in ref:
                 ref[key] = out['predictions'].clone()
             agree = float((out['predictions'] == ref[key]).float().mean())
-            print(json.dumps(dict(rows=rows, attn_pipe=pipe, ms_per_launch=round(ms, 3), captions_per_s=round(rows / ms * 1e3, 1),
+            print(json.dumps(dict(rows=rows, option=OPTION, value=pipe, ms_per_launch=round(ms, 3), captions_per_s=round(rows / ms * 1e3, 1),
                                   token_agreement_with_first_run=round(agree, 4))), flush=True)
