@@ -55,9 +55,14 @@ def generate_lineidx(tsv_file):
     if size == 0:
         offsets = np.zeros((0,), dtype='<i8')
     else:
+        chunks = [np.zeros((1,), dtype='<i8')]
+        step = 64 << 20                                     # scan 64 MiB at a time: image TSVs run to hundreds of GB
         with open(tsv_file, 'rb') as fp, mmap.mmap(fp.fileno(), 0, access=mmap.ACCESS_READ) as m:
-            nl = np.flatnonzero(np.frombuffer(m, dtype=np.uint8) == 10).astype('<i8')
-        starts = np.concatenate([np.zeros((1,), dtype='<i8'), nl + 1])
+            for lo in range(0, size, step):
+                view = np.frombuffer(m, dtype=np.uint8, count=min(step, size - lo), offset=lo)
+                chunks.append(np.flatnonzero(view == 10).astype('<i8') + (lo + 1))
+                del view
+        starts = np.concatenate(chunks)
         offsets = starts[starts < size]
     offsets.astype('<i8').tofile(lineidx_8b)
     with open(lineidx, 'w') as fp:
