@@ -44,6 +44,10 @@ CASES = {
     # run-time positional-embedding interpolation (reference layers/CLIP/model.py:245-251)
     'base_ratio_greedy': dict(param={'test_crop_size': 160, 'test_respect_ratio_max': 224}, variant='perturbed', batch=2,
                               frames=0, search='greedy', max_steps=12, image_hw=[160, 208]),
+    # the shipped GIT_BASE_VQAv2 / TEXTVQA geometry (aux_data/models/GIT_BASE_VQAv2/parameter.yaml): 480-crop model
+    # (30x30 grid embedding), a 480x640 input (30x40 grid = 1201 image tokens) and a question prefix
+    'base_vqa_ratio_greedy': dict(param={'test_crop_size': 480, 'test_respect_ratio_max': 640}, variant='perturbed', batch=1,
+                                  frames=1, search='greedy', max_steps=10, image_hw=[480, 640], prefix=[101, 2054, 2003, 2023]),
     # square non-default crop: the embedding is built for the 10x10 grid, no run-time interpolation
     'base_crop160_greedy': dict(param={'test_crop_size': 160}, variant='perturbed', batch=2, frames=1, search='greedy',
                                 max_steps=12, image_hw=[160, 160]),

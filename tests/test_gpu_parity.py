@@ -380,3 +380,13 @@ def test_experimental_kv_head_major_matches_default_layout(name):
         m.set_engine_option('kv_head_major', 0)
     torch.cuda.synchronize()
     assert (za - zb).abs().max().item() < 0.05
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('GITB200_TEST_EXPERIMENTAL'),
+                    reason='golden added without GPU time left in round 1: run with GITB200_TEST_EXPERIMENTAL=1, then move the '
+                           'case into the parametrised lists above')
+def test_experimental_vqa_geometry_480x640_with_prefix():
+    """The shipped GIT_BASE_VQAv2 geometry: 480-crop model, 480x640 pixels (30x40 grid, 1201 image tokens, positional
+    embedding re-sampled on the device), question prefix -- same checks as every other golden case."""
+    test_image_features_and_projection('base_vqa_ratio_greedy')
+    test_greedy_teacher_forced_against_reference('base_vqa_ratio_greedy')

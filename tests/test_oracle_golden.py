@@ -8,7 +8,7 @@ import git_oracle
 from helpers import load_golden, golden_inputs
 
 CASES = ['base_greedy_init', 'base_greedy', 'base_beam', 'base_prefix', 'vatex_greedy',
-         'large_greedy', 'large_beam', 'base_ratio_greedy', 'base_crop160_greedy']
+         'large_greedy', 'large_beam', 'base_ratio_greedy', 'base_crop160_greedy', 'base_vqa_ratio_greedy']
 
 
 @pytest.mark.parametrize('name', CASES)

@@ -3,7 +3,7 @@
 #   gpurun --timeout 600 -- 'bash tools/round2_first_call.sh'
 mkdir -p gpurun_out
 # 1. the gated tests of switches written blind at the end of round 1
-GITB200_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -k experimental > gpurun_out/experimental_tests.log 2>&1
+GITB200_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_gpu_parity.py -q -k experimental > gpurun_out/experimental_tests.log 2>&1
 tail -3 gpurun_out/experimental_tests.log
 # 2. does a contiguous (head-major) image K/V slice lift the decode attention off 0.4 of HBM peak?
 timeout 90 python tools/attn_ab.py kv_head_major > gpurun_out/kv_head_major_ab.txt 2>&1
