@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgitb200.so')
 SOURCES = ['gitb200.cu']
-DEPS = ['gitb200.cu', 'engine_api.inc', 'ptx.cuh', 'gemm.cuh', 'gemm2.cuh', 'skinny.cuh', 'rowops.cuh', 'attention.cuh',
+DEPS = ['gitb200.cu', 'engine_api.inc', 'ptx.cuh', 'gemm.cuh', 'gemm2.cuh', 'rowops.cuh', 'attention.cuh',
         'search.cuh', 'preproc.cuh', 'preproc_api.inc',
         os.path.join('..', '..', 'include', 'gitb200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -181,8 +181,10 @@ __global__ void __launch_bounds__(NW * 32) flash_attn_kernel(const AttnParams p)
 
 // ------------------------------------------------------------------------------------------------
 struct DecAttnParams {
-  float* qkv;                      // [R, 3*D] fp32 (q | k | v): split-K accumulation buffer, zeroed after reading
-  const float* bqkv;               // [3*D] bias added here and qkv re-zeroed (split-K producer); null: qkv is final
+  const float* qkv;                // [n_partials][R, 3*D] fp32 (q | k | v): the QKV GEMM's split-K partial sums, added
+  int n_partials;                  //   here in split order (1..4 buffers, partial_stride elements apart)
+  long long partial_stride;
+  const float* bqkv;               // [3*D] bias, added here
   const __nv_bfloat16* img_k;      // [B, M, D]
   const __nv_bfloat16* img_v;
   __nv_bfloat16* txt_k;            // [R, T_alloc, D]
@@ -194,8 +196,6 @@ struct DecAttnParams {
   int pos_fixed;
   int chunk_rows;                  // image keys staged per TMA round (<= 512), box_rows * n_boxes
   int box_rows;                    // rows per TMA box (<= 256)
-  int head_major;                  // image K/V cache layout: 0 = [B][M][D] (128-byte slices at a D*2-byte pitch),
-                                   //                         1 = [B][H][M][64] (one (image, head) slice is contiguous)
   ChainSync chain;
 };
 
@@ -204,6 +204,15 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
   f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
   f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// One q / k / v element of this step: the split-K partial sums in split order (fixed order: bit-reproducible).
+__device__ __forceinline__ float ld_partials(const float* ptr, int n, long long stride) {
+  const float a = __ldcg(ptr);
+  const float b = n > 1 ? __ldcg(ptr + stride) : 0.f;
+  const float c = n > 2 ? __ldcg(ptr + 2 * stride) : 0.f;
+  const float d = n > 3 ? __ldcg(ptr + 3 * stride) : 0.f;
+  return ((a + b) + c) + d;
 }
 
 // Online-softmax state of one 8-lane key group for one query: running max m, running sum l, 8 output dims.
@@ -280,8 +289,8 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     const int nb = (rows_c + p.box_rows - 1) / p.box_rows;
     mbar_arrive_expect_tx(&bars[u & 1], static_cast<uint32_t>(2 * nb * p.box_rows * 128));
     for (int i = 0; i < nb; ++i) {
-      const int grow = (p.head_major ? (b * H + h) * p.M : b * p.M) + c * p.chunk_rows + i * p.box_rows;
-      const int gcol = p.head_major ? 0 : h * 64;
+      const int grow = b * p.M + c * p.chunk_rows + i * p.box_rows;
+      const int gcol = h * 64;
       tma_load_2d(sK + static_cast<size_t>(i) * p.box_rows * 128, &tmK, &bars[u & 1], gcol, grow);
       tma_load_2d(sV + static_cast<size_t>(i) * p.box_rows * 128, &tmV, &bars[u & 1], gcol, grow);
     }
@@ -299,7 +308,6 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     griddep_wait();
     finished = (p.state != nullptr && p.state->finished);
   }
-  griddep_launch_late();
   if (finished) {  // never leave with a bulk copy in flight into this CTA's shared memory
     mbar_wait(&bars[0], 0);
     if (n_units > 1) mbar_wait(&bars[1], 0);
@@ -326,10 +334,10 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       const int b = item / H, h = item - b * H;
       const float* row = p.qkv + static_cast<long long>(b) * 3 * D + h * 64;
       if (tid < 64) {
-        pre_a[k] = __ldcg(row + tid);
-        pre_b[k] = __ldcg(row + D + tid);
+        pre_a[k] = ld_partials(row + tid, p.n_partials, p.partial_stride);
+        pre_b[k] = ld_partials(row + D + tid, p.n_partials, p.partial_stride);
       } else {
-        pre_a[k] = __ldcg(row + 2 * D + tid - 64);
+        pre_a[k] = ld_partials(row + 2 * D + tid - 64, p.n_partials, p.partial_stride);
       }
     }
   }
@@ -342,10 +350,10 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       const int b = item / H, h = item - b * H;
       const float* row = p.qkv + static_cast<long long>(b) * 3 * D + h * 64;
       if (tid < 64) {
-        a = __ldcg(row + tid);
-        b2 = __ldcg(row + D + tid);
+        a = ld_partials(row + tid, p.n_partials, p.partial_stride);
+        b2 = ld_partials(row + D + tid, p.n_partials, p.partial_stride);
       } else {
-        a = __ldcg(row + 2 * D + tid - 64);
+        a = ld_partials(row + 2 * D + tid - 64, p.n_partials, p.partial_stride);
       }
     }
   };
@@ -363,24 +371,18 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     // ---- q (scaled by 1/8 in fp32 like the reference scales Q), append this step's K/V (bf16) ----
     for (int qi = 0; qi < NQ; ++qi) {
       const int r = b * NQ + qi;
-      float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
-      const float* bias = (p.bqkv != nullptr ? p.bqkv : p.qkv) + h * 64;  // never dereferenced when bqkv == null
+      const float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
+      const float* bias = p.bqkv + h * 64;
       const bool have = (NQ == 1) && (k < kPre);
-      const bool acc_mode = p.bqkv != nullptr;
       if (tid < 64) {
-        const float qv = have ? pre_a[k < kPre ? k : 0] : (kPipeOn ? cur_a : __ldcg(row + tid));
-        const float kv = have ? pre_b[k < kPre ? k : 0] : (kPipeOn ? cur_b : __ldcg(row + D + tid));
-        q_s[qi][tid] = (qv + (acc_mode ? bias[tid] : 0.f)) * 0.125f;
-        p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(kv + (acc_mode ? bias[D + tid] : 0.f));
-        if (acc_mode) {
-          row[tid] = 0.f;
-          row[D + tid] = 0.f;
-        }
+        const float qv = have ? pre_a[k < kPre ? k : 0] : (kPipeOn ? cur_a : ld_partials(row + tid, p.n_partials, p.partial_stride));
+        const float kv = have ? pre_b[k < kPre ? k : 0] : (kPipeOn ? cur_b : ld_partials(row + D + tid, p.n_partials, p.partial_stride));
+        q_s[qi][tid] = (qv + bias[tid]) * 0.125f;
+        p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + tid] = __float2bfloat16_rn(kv + bias[D + tid]);
       } else {
         const int d = tid - 64;
-        const float vv = have ? pre_a[k < kPre ? k : 0] : (kPipeOn ? cur_a : __ldcg(row + 2 * D + d));
-        p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(vv + (acc_mode ? bias[2 * D + d] : 0.f));
-        if (acc_mode) row[2 * D + d] = 0.f;
+        const float vv = have ? pre_a[k < kPre ? k : 0] : (kPipeOn ? cur_a : ld_partials(row + 2 * D + d, p.n_partials, p.partial_stride));
+        p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = __float2bfloat16_rn(vv + bias[2 * D + d]);
       }
     }
     __syncthreads();
@@ -531,25 +533,6 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   }
   tl_mark(200003);
   chain_signal(p.chain);
-}
-
-// Image K/V cache [n][B][M][D] (n = layers x {K, V}; what the prefill GEMM epilogue writes) -> [n][B][H][M][64]: the slice
-// one decode-attention item streams becomes one contiguous M x 128-byte run instead of M 128-byte pieces at a D*2-byte
-// pitch. One thread per 16 bytes; once per generate call (the cache is read 39 x 6 times afterwards).
-__global__ void __launch_bounds__(256)
-kv_head_major_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n_img, int M, int H) {
-  const long long per_img = static_cast<long long>(M) * H * 8;      // 16-byte units per image
-  const long long total = n_img * per_img;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long img = i / per_img;
-    const long long r = i - img * per_img;
-    const int m = static_cast<int>(r / (H * 8));
-    const int c = static_cast<int>(r - static_cast<long long>(m) * (H * 8));
-    const int hh = c >> 3, l8 = c & 7;
-    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
-    reinterpret_cast<uint4*>(dst)[img * per_img + (static_cast<long long>(hh) * M + m) * 8 + l8] = v;
-  }
 }
 
 }  // namespace gitb200

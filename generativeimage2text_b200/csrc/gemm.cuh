@@ -12,8 +12,9 @@
 //   normal     : out[row_map(m)][n] (+bias[n]) (+act) (+resid[m][n]); N may be split into up to three equal
 //                column segments with their own base pointers (QKV -> q scratch / K cache / V cache).
 //   transposed : "swap-AB" for the skinny decode-step GEMMs: A = weight [features, K], B = activations
-//                [rows<=BN, K]; out[n][m] (+bias[m]) (+act), optionally accumulated with fp32 atomics when
-//                the K dimension is split over CTAs so a handful of rows still spreads over many SMs.
+//                [rows<=BN, K]; out[n][m] (+bias[m]) (+act).  When the K dimension is split over CTAs (so a handful
+//                of rows still spreads over many SMs) every split writes its own partial-sum buffer and the consumer
+//                kernel adds them in split order: results are bit-reproducible from run to run.
 #pragma once
 #include "ptx.cuh"
 
@@ -23,7 +24,9 @@ struct GemmParams {
   int M, N, K;
   int k_splits;
   int transposed;             // epilogue shape / options below select the kernel instantiation on the host
-  int atomic;
+  int partial;                // split-K: split s stores its partial sums at out[0] + s * split_stride (plain stores; the
+                              // consumer adds the partials in split order -> bit-reproducible, no atomics, no zeroing)
+  long long split_stride;     // elements between the partial buffers of consecutive splits
   int act;
   int out_bf16;
   const float* bias;
@@ -43,9 +46,9 @@ struct GemmParams {
 
 // Epilogue variants are compile-time (the runtime-flag version spent ~700 warp instructions per 32x32 chunk,
 // which made every K=768 GEMM of the encoder epilogue-issue bound).
-constexpr int EPI_TRANSPOSED = 1, EPI_BF16 = 2, EPI_RESID = 4, EPI_ATOMIC = 8, EPI_ACT_SHIFT = 4, EPI_DIRECT = 64;
-constexpr int epi_code(bool transposed, bool bf16, bool resid, bool atomic, int act) {
-  return (transposed ? EPI_TRANSPOSED : 0) | (bf16 ? EPI_BF16 : 0) | (resid ? EPI_RESID : 0) | (atomic ? EPI_ATOMIC : 0) |
+constexpr int EPI_TRANSPOSED = 1, EPI_BF16 = 2, EPI_RESID = 4, EPI_PARTIAL = 8, EPI_ACT_SHIFT = 4;
+constexpr int epi_code(bool transposed, bool bf16, bool resid, bool partial, int act) {
+  return (transposed ? EPI_TRANSPOSED : 0) | (bf16 ? EPI_BF16 : 0) | (resid ? EPI_RESID : 0) | (partial ? EPI_PARTIAL : 0) |
          (act << EPI_ACT_SHIFT);
 }
 
@@ -76,6 +79,84 @@ struct GemmCfg {
   static_assert(STAGES >= 3, "pipeline depth");
 };
 
+// ---- epilogue building blocks shared by the 1-CTA kernel below and the CTA-pair kernel of gemm2.cuh --------------------
+// Output row offsets (elements) of the 8 rows a lane stores in the normal epilogue: rows row0 + it * 4 + (lane >> 3).
+__device__ __forceinline__ uint32_t epi_row_offsets(const GemmParams& p, int row0, int rsub, bool store_ok, long long (&ooff)[8]) {
+  uint32_t okmask = 0;
+  int bq = (row0 + rsub) / p.rows_per_batch;
+  int sq = (row0 + rsub) - bq * p.rows_per_batch;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    if (row0 + it * 4 + rsub < p.M && store_ok) okmask |= 1u << it;
+    ooff[it] = (static_cast<long long>(bq) * p.batch_stride + sq + p.row_offset) * p.ldo;
+    sq += 4;
+    while (sq >= p.rows_per_batch) { sq -= p.rows_per_batch; ++bq; }
+  }
+  return okmask;
+}
+
+// Normal epilogue of one 32x32 fp32 accumulator chunk (thread = row after tcgen05.ld): transpose through the warp's
+// swizzled staging buffer so that each lane ends up with 4 consecutive output elements of one row (coalesced 128-bit
+// accesses), then (+bias) (+act) (+residual) -> bf16 / fp32 stores into the chunk's column segment.
+template <int EPI>
+__device__ __forceinline__ void epi_store_normal(const GemmParams& p, const uint32_t (&r)[32], uint8_t* stg, int lane, int n0,
+                                                 int row0, const long long (&ooff)[8], uint32_t okmask) {
+  constexpr bool kBf16 = (EPI & EPI_BF16) != 0;
+  constexpr bool kResid = (EPI & EPI_RESID) != 0;
+  constexpr int kAct = (EPI >> EPI_ACT_SHIFT) & 3;
+  const int c4 = lane & 7;
+  const int rsub = lane >> 3;
+  // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+  // phase 2: 8 lanes per row (4 columns each), 4 rows per instruction
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + c4);
+  int seg = 0;
+  if (p.seg_n < p.N) seg = n0 / p.seg_n;
+  const int nn = n0 - seg * p.seg_n + c4 * 4;
+  float4 v[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rsub;
+    v[it] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+  }
+  float4 res[8];
+  if (kResid) {
+    const float* rbase = p.resid + static_cast<long long>(row0 + rsub) * p.ld_resid + n0 + c4 * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (okmask & (1u << it)) res[it] = *reinterpret_cast<const float4*>(rbase + static_cast<long long>(it) * 4 * p.ld_resid);
+    }
+  }
+  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out[seg]) + static_cast<long long>(nn) * (kBf16 ? 2 : 4);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    float4 o = v[it];
+    o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+    if (kAct != ACT_NONE) {
+      o.x = act_ct<kAct>(o.x); o.y = act_ct<kAct>(o.y); o.z = act_ct<kAct>(o.z); o.w = act_ct<kAct>(o.w);
+    }
+    if (kResid) {   // out = resid + (acc + bias): the operand order of the reference's `x + f(x)`
+      o.x = res[it].x + o.x; o.y = res[it].y + o.y; o.z = res[it].z + o.z; o.w = res[it].w + o.w;
+    }
+    if (okmask & (1u << it)) {
+      if (kBf16) {
+        uint2 pk;
+        pk.x = pack_bf16(o.x, o.y);
+        pk.y = pack_bf16(o.z, o.w);
+        *reinterpret_cast<uint2*>(obase + ooff[it] * 2) = pk;
+      } else {
+        *reinterpret_cast<float4*>(obase + ooff[it] * 4) = o;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -83,10 +164,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using C = GemmCfg<BN>;
   constexpr bool kTransposed = (EPI & EPI_TRANSPOSED) != 0;
   constexpr bool kBf16 = (EPI & EPI_BF16) != 0;
-  constexpr bool kResid = (EPI & EPI_RESID) != 0;
-  constexpr bool kAtomic = (EPI & EPI_ATOMIC) != 0;
+  constexpr bool kPartial = (EPI & EPI_PARTIAL) != 0;
   constexpr int kAct = (EPI >> EPI_ACT_SHIFT) & 3;
-  constexpr bool kDirect = (EPI & EPI_DIRECT) != 0;   // thread = row, registers -> global (no smem transpose)
   if (p.pdl) griddep_launch_early();
   if (p.pdl) tl_mark(100000 + 1000 + static_cast<int>(gridDim.x));
   // `skip` (decode finished) only changes between steps, which are separated by full dependencies
@@ -105,8 +184,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool dbg = (p.dbg != nullptr) && blockIdx.x == 0;
-  if (dbg && threadIdx.x == 0) p.dbg[0] = globaltimer_ns();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -131,7 +208,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();
 
   const int m_tiles = (p.M + C::BM - 1) / C::BM;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -158,7 +234,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (chained) chain_wait(p.chain);
   else if (p.pdl) griddep_wait();
-  if (p.pdl) griddep_launch_late();
   if (p.pdl) tl_mark(1000 + static_cast<int>(gridDim.x));
 
   if (warp == 0) {
@@ -208,7 +283,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (dbg && tile == 0 && kb == kb0) p.dbg[2] = globaltimer_ns();
           if (p.pdl && tile == static_cast<int>(blockIdx.x) && kb == kb0) tl_mark_one(300000 + 1000 + static_cast<int>(gridDim.x));
           const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
           const uint32_t b_base = smem_u32(sB + stage * C::B_BYTES);
@@ -224,7 +298,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         umma_commit(&tfull[accum]);  // accumulator complete -> epilogue
-        if (dbg && tile == 0) p.dbg[3] = globaltimer_ns();
         accum ^= 1;
         if (accum == 0) accum_phase ^= 1;
       }
@@ -240,7 +313,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* stg = sStage + (warp - 4) * (32 * 128);
     const int c4 = lane & 7;
     const int rsub = lane >> 3;
-    const bool single_seg = p.seg_n >= p.N;
     int accum = 0;
     uint32_t accum_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -252,27 +324,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ---- per-tile row bookkeeping (normal mode): output row offsets of this lane's 8 rows ----
       long long ooff[8];
       uint32_t okmask = 0;
-      long long drow_off = 0;   // direct epilogue: output row offset of this thread's row (row0 + lane)
-      bool drow_ok = false;
-      if (!kTransposed && kDirect) {
-        const int row = row0 + lane;
-        const int bq = row / p.rows_per_batch;
-        drow_off = (static_cast<long long>(bq) * p.batch_stride + (row - bq * p.rows_per_batch) + p.row_offset) * p.ldo;
-        drow_ok = row < p.M && store_ok;
-      } else if (!kTransposed) {
-        int bq = (row0 + rsub) / p.rows_per_batch;
-        int sq = (row0 + rsub) - bq * p.rows_per_batch;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (row0 + it * 4 + rsub < p.M && store_ok) okmask |= 1u << it;
-          ooff[it] = (static_cast<long long>(bq) * p.batch_stride + sq + p.row_offset) * p.ldo;
-          sq += 4;
-          while (sq >= p.rows_per_batch) { sq -= p.rows_per_batch; ++bq; }
-        }
-      }
+      if (!kTransposed) okmask = epi_row_offsets(p, row0, rsub, store_ok, ooff);
       mbar_wait(&tfull[accum], accum_phase);
       tc_fence_after();
-      if (dbg && tile == 0 && warp == 4 && lane == 0) p.dbg[4] = globaltimer_ns();
       if (p.pdl && tile == static_cast<int>(blockIdx.x) && warp == 4 && lane == 0) tl_mark_one(400000 + 1000 + static_cast<int>(gridDim.x));
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -281,97 +335,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN + c * 32, r);
         tmem_ld_wait();
-        if (!kTransposed && kDirect) {
-          // thread = row: 32 consecutive outputs of one row straight from registers (64 B bf16 / 128 B fp32 per lane).
-          // Fewer instructions than the staged transpose (no STS/LDS/syncwarp), paid with 32 L1 wavefronts per store.
-          int seg = 0;
-          if (!single_seg) seg = n0 / p.seg_n;
-          const int nn = n0 - seg * p.seg_n;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(bp + j);
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-          }
-          if (kAct != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_ct<kAct>(v[j]);
-          }
-          if (drow_ok) {
-            if (kResid) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row0 + lane) * p.ld_resid + n0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r4 = rp[j];
-                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-              }
-            }
-            if (kBf16) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + drow_off + nn);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            } else {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + drow_off + nn);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-          }
-        } else if (!kTransposed) {
-          // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          __syncwarp();
-          // phase 2: 8 lanes per row (4 columns each), 4 rows per instruction
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + c4);
-          int seg = 0;
-          if (!single_seg) seg = n0 / p.seg_n;
-          const int nn = n0 - seg * p.seg_n + c4 * 4;
-          float4 v[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            v[it] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-          }
-          if (kResid) {
-            const float* rbase = p.resid + static_cast<long long>(row0 + rsub) * p.ld_resid + n0 + c4 * 4;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              if (okmask & (1u << it)) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rbase + static_cast<long long>(it) * 4 * p.ld_resid);
-                v[it].x += r4.x; v[it].y += r4.y; v[it].z += r4.z; v[it].w += r4.w;
-              }
-            }
-          }
-          uint8_t* obase = reinterpret_cast<uint8_t*>(p.out[seg]) + static_cast<long long>(nn) * (kBf16 ? 2 : 4);
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            float4 o = v[it];
-            // bias and activation come before the residual in every caller that uses both (resid => act none)
-            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-            if (kAct != ACT_NONE) {
-              o.x = act_ct<kAct>(o.x); o.y = act_ct<kAct>(o.y); o.z = act_ct<kAct>(o.z); o.w = act_ct<kAct>(o.w);
-            }
-            if (okmask & (1u << it)) {
-              if (kBf16) {
-                uint2 pk;
-                pk.x = pack_bf16(o.x, o.y);
-                pk.y = pack_bf16(o.z, o.w);
-                *reinterpret_cast<uint2*>(obase + ooff[it] * 2) = pk;
-              } else {
-                *reinterpret_cast<float4*>(obase + ooff[it] * 4) = o;
-              }
-            }
-          }
-          __syncwarp();
+        if (!kTransposed) {
+          epi_store_normal<EPI>(p, r, stg, lane, n0, row0, ooff, okmask);
         } else {
           // transposed ("swap-AB"): lane = output feature, register j = activation row n0 + j.  Stage the 32x32
           // chunk as [activation row][feature] so that each lane then owns 4 consecutive features of one row:
@@ -400,13 +365,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (arow < p.N && store_ok && f0 < p.M) {
               const long long off = static_cast<long long>(arow) * p.ldo + f0;
-              if (kAtomic) {
-                float* dst = reinterpret_cast<float*>(p.out[0]) + off;
-                if (full4) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+              if (kPartial) {   // this split's own partial-sum buffer (plain stores; summed in split order by the consumer)
+                float* dst = reinterpret_cast<float*>(p.out[0]) + static_cast<long long>(split) * p.split_stride + off;
+                if (full4 && (p.ldo & 3) == 0) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 } else {
                   for (int e = 0; e < 4; ++e)
-                    if (f0 + e < p.M) atomicAdd(dst + e, v[e]);
+                    if (f0 + e < p.M) dst[e] = v[e];
                 }
               } else if (kBf16) {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[0]) + off;
@@ -448,7 +413,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (p.pdl) tl_mark(200000 + 1000 + static_cast<int>(gridDim.x));
   if (chained && threadIdx.x == 0) chain_signal_thread0(p.chain);
-  if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);

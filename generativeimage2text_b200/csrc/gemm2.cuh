@@ -9,7 +9,7 @@
 //     a plain remote arrive (full barrier count 2);
 //   * tcgen05.commit.cta_group::2 ... multicast::cluster signals `empty` / `tmem full` in both CTAs;
 //   * each CTA's 8 epilogue warps drain their own 128 TMEM lanes; all 16 warps arrive on the leader's `tmem empty`.
-// Normal (non-transposed) epilogues only; the epilogue body is the same as in gemm.cuh.
+// Normal (non-transposed) epilogues only; the epilogue body is gemm.cuh's epi_store_normal().
 #pragma once
 #include "gemm.cuh"
 
@@ -87,13 +87,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN>::THREAD
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmParams p) {
   using C = Gemm2Cfg<BN>;
-  constexpr bool kTransposed = false;
-  static_assert((EPI & EPI_TRANSPOSED) == 0, "2-CTA kernel: normal epilogues only");
-  constexpr bool kBf16 = (EPI & EPI_BF16) != 0;
-  constexpr bool kResid = (EPI & EPI_RESID) != 0;
-  constexpr bool kAtomic = (EPI & EPI_ATOMIC) != 0;
-  constexpr int kAct = (EPI >> EPI_ACT_SHIFT) & 3;
-  constexpr bool kDirect = (EPI & EPI_DIRECT) != 0;
+  static_assert((EPI & (EPI_TRANSPOSED | EPI_PARTIAL)) == 0, "2-CTA kernel: normal epilogues only");
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -214,40 +208,17 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // that each lane ends up with 4 consecutive output elements of one row: coalesced 128-bit accesses.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    const bool store_ok = true;
     uint8_t* stg = sStage + (warp - 4) * (32 * 128);
-    const int c4 = lane & 7;
     const int rsub = lane >> 3;
-    const bool single_seg = p.seg_n >= p.N;
     int accum = 0;
     uint32_t accum_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int split = tile / mn_tiles;
-      const int rem = tile - split * mn_tiles;
+      const int rem = tile % mn_tiles;
       const int m_blk = rem / n_tiles;
       const int n_blk = rem - m_blk * n_tiles;
       const int row0 = m_blk * 2 * C::BM + static_cast<int>(rank) * C::BM + q * 32;  // first tile row of this warp
-      // ---- per-tile row bookkeeping (normal mode): output row offsets of this lane's 8 rows ----
       long long ooff[8];
-      uint32_t okmask = 0;
-      long long drow_off = 0;   // direct epilogue: output row offset of this thread's row (row0 + lane)
-      bool drow_ok = false;
-      if (!kTransposed && kDirect) {
-        const int row = row0 + lane;
-        const int bq = row / p.rows_per_batch;
-        drow_off = (static_cast<long long>(bq) * p.batch_stride + (row - bq * p.rows_per_batch) + p.row_offset) * p.ldo;
-        drow_ok = row < p.M && store_ok;
-      } else if (!kTransposed) {
-        int bq = (row0 + rsub) / p.rows_per_batch;
-        int sq = (row0 + rsub) - bq * p.rows_per_batch;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (row0 + it * 4 + rsub < p.M && store_ok) okmask |= 1u << it;
-          ooff[it] = (static_cast<long long>(bq) * p.batch_stride + sq + p.row_offset) * p.ldo;
-          sq += 4;
-          while (sq >= p.rows_per_batch) { sq -= p.rows_per_batch; ++bq; }
-        }
-      }
+      const uint32_t okmask = epi_row_offsets(p, row0, rsub, true, ooff);
       mbar_wait(&tfull[accum], accum_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -257,160 +228,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN + c * 32, r);
         tmem_ld_wait();
-        if (!kTransposed && kDirect) {
-          // thread = row: 32 consecutive outputs of one row straight from registers (64 B bf16 / 128 B fp32 per lane).
-          // Fewer instructions than the staged transpose (no STS/LDS/syncwarp), paid with 32 L1 wavefronts per store.
-          int seg = 0;
-          if (!single_seg) seg = n0 / p.seg_n;
-          const int nn = n0 - seg * p.seg_n;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(bp + j);
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-          }
-          if (kAct != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_ct<kAct>(v[j]);
-          }
-          if (drow_ok) {
-            if (kResid) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row0 + lane) * p.ld_resid + n0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r4 = rp[j];
-                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-              }
-            }
-            if (kBf16) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out[seg]) + drow_off + nn);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            } else {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out[seg]) + drow_off + nn);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-          }
-        } else if (!kTransposed) {
-          // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          __syncwarp();
-          // phase 2: 8 lanes per row (4 columns each), 4 rows per instruction
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + c4);
-          int seg = 0;
-          if (!single_seg) seg = n0 / p.seg_n;
-          const int nn = n0 - seg * p.seg_n + c4 * 4;
-          float4 v[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            v[it] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-          }
-          if (kResid) {
-            const float* rbase = p.resid + static_cast<long long>(row0 + rsub) * p.ld_resid + n0 + c4 * 4;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              if (okmask & (1u << it)) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rbase + static_cast<long long>(it) * 4 * p.ld_resid);
-                v[it].x += r4.x; v[it].y += r4.y; v[it].z += r4.z; v[it].w += r4.w;
-              }
-            }
-          }
-          uint8_t* obase = reinterpret_cast<uint8_t*>(p.out[seg]) + static_cast<long long>(nn) * (kBf16 ? 2 : 4);
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            float4 o = v[it];
-            // bias and activation come before the residual in every caller that uses both (resid => act none)
-            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-            if (kAct != ACT_NONE) {
-              o.x = act_ct<kAct>(o.x); o.y = act_ct<kAct>(o.y); o.z = act_ct<kAct>(o.z); o.w = act_ct<kAct>(o.w);
-            }
-            if (okmask & (1u << it)) {
-              if (kBf16) {
-                uint2 pk;
-                pk.x = pack_bf16(o.x, o.y);
-                pk.y = pack_bf16(o.z, o.w);
-                *reinterpret_cast<uint2*>(obase + ooff[it] * 2) = pk;
-              } else {
-                *reinterpret_cast<float4*>(obase + ooff[it] * 4) = o;
-              }
-            }
-          }
-          __syncwarp();
-        } else {
-          // transposed ("swap-AB"): lane = output feature, register j = activation row n0 + j.  Stage the 32x32
-          // chunk as [activation row][feature] so that each lane then owns 4 consecutive features of one row:
-          // 128-bit stores / vector reductions (a warp-wide scalar RED costs ~1.3 cycles per lane on the LSU).
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            *reinterpret_cast<uint32_t*>(stg + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + ((lane & 3) << 2)) = r[j];
-          __syncwarp();
-          const int f0 = row0 + c4 * 4;  // first of this lane's 4 features
-          const bool full4 = (f0 + 3) < p.M;
-          float bv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (p.bias != nullptr && split == 0) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (f0 + e < p.M) bv[e] = __ldg(p.bias + f0 + e);
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            const int arow = n0 + rr;
-            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-            float v[4] = {t4.x + bv[0], t4.y + bv[1], t4.z + bv[2], t4.w + bv[3]};
-            if (kAct != ACT_NONE) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = act_ct<kAct>(v[e]);
-            }
-            if (arow < p.N && store_ok && f0 < p.M) {
-              const long long off = static_cast<long long>(arow) * p.ldo + f0;
-              if (kAtomic) {
-                float* dst = reinterpret_cast<float*>(p.out[0]) + off;
-                if (full4) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (f0 + e < p.M) atomicAdd(dst + e, v[e]);
-                }
-              } else if (kBf16) {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[0]) + off;
-                if (full4 && (p.ldo & 3) == 0) {
-                  uint2 pk;
-                  pk.x = pack_bf16(v[0], v[1]);
-                  pk.y = pack_bf16(v[2], v[3]);
-                  *reinterpret_cast<uint2*>(dst) = pk;
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (f0 + e < p.M) dst[e] = __float2bfloat16_rn(v[e]);
-                }
-              } else {
-                float* dst = reinterpret_cast<float*>(p.out[0]) + off;
-                if (full4 && (p.ldo & 3) == 0) {
-                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                } else if (full4 && (p.ldo & 1) == 0) {
-                  *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-                  *reinterpret_cast<float2*>(dst + 2) = make_float2(v[2], v[3]);
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (f0 + e < p.M) dst[e] = v[e];
-                }
-              }
-            }
-          }
-          __syncwarp();
-        }
+        epi_store_normal<EPI>(p, r, stg, lane, n0, row0, ooff, okmask);
       }
       tc_fence_before();
       __syncwarp();

@@ -34,7 +34,6 @@
 #include "ptx.cuh"
 #include "rowops.cuh"
 #include "search.cuh"
-#include "skinny.cuh"
 
 using namespace gitb200;
 typedef __nv_bfloat16 bf16;
@@ -109,23 +108,7 @@ struct gitb200_engine {
   bool use_graph = true;
   bool use_pdl = true;
   bool use_chain = true;
-  // decode GEMMs through skinny.cuh (mma.sync, fewer dependent hops per CTA) instead of swap-AB tcgen05. Measured on
-  // B200 (bench.py, 10 steps): 18.89 ms/step lean vs 18.09 ms tcgen05 -> off by default, kept for comparison.
-  bool use_lean = false;
-  int decode_ctas = 0;    // cap on CTAs per decode-step kernel (0 = none): smaller footprints let the chains of several
-                          // batches in flight overlap instead of serialising on the 148-CTA LM head / 296-CTA attention
-  int sm_reserve = 0;     // SMs the persistent encoder / prefill GEMMs leave free (for decode chains of other batches in flight)
-  bool epi_direct = false; // measured: the staged transpose is faster on every ViT shape (direct stores are LSU bound)
-  // (kept switchable)   // normal-mode GEMM epilogue: registers -> global (true) or staged smem transpose (false)
   bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
-  bool kv_head_major = false;   // decode attention reads a head-major copy of the image K/V cache (contiguous slices);
-                                // built blind at the end of round 1 (no GPU budget left): off until measured
-  bool attn_pipe = true;  // decode attention with software-pipelined q/k/v and text K/V requests (attention.cuh kPipe)
-  bool prio_split = false; // decode loop on an engine-owned HIGH-priority stream (encoder / prefill stay on the caller's):
-                          // with several batches in flight the short decode kernels are dispatched ahead of the waves of
-                          // another batch's encoder kernels
-  cudaStream_t prio_stream = nullptr;
-  cudaEvent_t prio_ev[2] = {nullptr, nullptr};
   const gitb200_engine* weights_from = nullptr;   // non-null: weight buffers are borrowed from that engine
 
   // derived geometry
@@ -145,7 +128,7 @@ struct gitb200_engine {
   // workspaces
   DevBuf x, h, qkv, ctx, u, feats, feats_f32, pos_interp;   // encoder
   DevBuf pt, pxd, phd, pq, pctx, pu;                        // prefill
-  DevBuf img_kv, img_kv_hm, txt_kv, src_row[2];             // caches (img_kv_hm: head-major copy, option kv_head_major)
+  DevBuf img_kv, txt_kv, src_row[2];                        // caches
   DevBuf xd_t, hd_t, qkv_t, ctx_t, t_t, u_t, logits;        // decode step
   DevBuf state, next_token, logprob_sum, tokens_i64, stage_img, stage_tok, stage_lp, prefix_dev;
   DevBuf beam_ws;                                           // beam-search bookkeeping (search.cuh)
@@ -168,23 +151,17 @@ struct gitb200_engine {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t own_event = nullptr;
   // asynchronous generate: enqueue now, read the loop state back in gitb200_generate_finish
-  StepState* host_state = nullptr;   // pinned [kMaxLanes]
+  StepState* host_state = nullptr;   // pinned
   bool pending = false;
-  int pend_lanes = 1, pend_max_steps = 0;
+  int pend_max_steps = 0;
   bool pend_beam = false;
   cudaStream_t pend_stream = nullptr;
+  cudaEvent_t chunk_ev[2] = {nullptr, nullptr};   // decode-loop chunks (generate_impl)
   int64_t* pend_tok_host = nullptr;  // host-buffer variant: results land here
-  // decode lanes: the greedy batch is split into independent row groups whose (latency-bound) kernel chains run
-  // concurrently on separate streams -- forked and joined inside the captured step graph
-  int lanes_opt = 1;   // measured: the chains are latency bound, concurrent lanes do not shorten a step (kept as an option)
-  cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr;
-  cudaEvent_t ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
-constexpr int kMaxLanes = 4;
+// Row range of one decode chain (the whole batch; kept as a struct so that step_layers reports its chain tail).
 struct Lane {
-  int idx = 0;
   int row0 = 0, rows = 0;   // sequences (images * beam)
   int b0 = 0, nb = 0;       // images
   cudaStream_t st = nullptr;
@@ -311,9 +288,7 @@ static int launch_gemm_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t s
   const int m_tiles = (c.p.M + 127) / 128;
   const int n_tiles = (c.p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles * c.p.k_splits;
-  int sms = (c.p.transposed || c.p.M < 2048) ? h->num_sms : h->num_sms - h->sm_reserve;
-  if (c.p.transposed && h->decode_ctas > 0 && h->decode_ctas < sms) sms = h->decode_ctas;
-  const int grid = tiles < sms ? tiles : sms;
+  const int grid = tiles < h->num_sms ? tiles : h->num_sms;
   h->last_gemm_grid = grid;
   CK(launch_k(c.p.pdl != 0, gemm_bf16_tcgen05<BN, EPI>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
   CKL(h, "gemm_bf16_tcgen05");
@@ -334,50 +309,38 @@ static int launch_gemm2_inst(gitb200_engine* h, const GemmCall& c, cudaStream_t 
   const int m_tiles = (c.p.M + 255) / 256;
   const int n_tiles = (c.p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
-  const int pairs = std::min(tiles, (h->num_sms - h->sm_reserve) / 2);
+  const int pairs = std::min(tiles, h->num_sms / 2);
   h->last_gemm_grid = 2 * pairs;
   CK(launch_k(false, gemm2_bf16_tcgen05<BN, EPI>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, c.p));
   CKL(h, "gemm2_bf16_tcgen05");
   return 0;
 }
+// The epilogue variants the hot path uses (each is its own kernel instantiation).
 template <int BN>
 static int launch_gemm2_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
   const GemmParams& p = c.p;
-  const int code = epi_code(false, p.out_bf16 != 0, p.resid != nullptr, false, p.act) | (h->epi_direct ? EPI_DIRECT : 0);
-  switch (code) {
+  switch (epi_code(false, p.out_bf16 != 0, p.resid != nullptr, false, p.act)) {
     case epi_code(false, true, false, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_NONE)>(h, c, st);
-      case epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
     case epi_code(false, false, true, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, false, true, false, ACT_NONE)>(h, c, st);
-      case epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
     case epi_code(false, false, false, false, ACT_NONE): return launch_gemm2_inst<BN, epi_code(false, false, false, false, ACT_NONE)>(h, c, st);
-      case epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
     case epi_code(false, true, false, false, ACT_QUICKGELU): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU)>(h, c, st);
-      case epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT>(h, c, st);
     case epi_code(false, true, false, false, ACT_GELU_ERF): return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF)>(h, c, st);
-      case epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT: return launch_gemm2_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT>(h, c, st);
     default: break;
   }
   return fail(h, "gemm2: epilogue combination not instantiated");
 }
 
-// The epilogue variants the hot path uses (each is its own kernel instantiation).
 template <int BN>
 static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
   const GemmParams& p = c.p;
-  const int code = epi_code(p.transposed != 0, p.out_bf16 != 0, p.resid != nullptr, p.atomic != 0, p.act) |
-                   ((h->epi_direct && !p.transposed) ? EPI_DIRECT : 0);
+  const int code = epi_code(p.transposed != 0, p.out_bf16 != 0, p.resid != nullptr, p.partial != 0, p.act);
   if constexpr (BN == 192 || BN == 256 || BN == 128) {
     switch (code) {
       case epi_code(false, true, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_NONE)>(h, c, st);
-      case epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
       case epi_code(false, false, true, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, false, true, false, ACT_NONE)>(h, c, st);
-      case epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, false, true, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
       case epi_code(false, false, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, false, false, false, ACT_NONE)>(h, c, st);
-      case epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, false, false, false, ACT_NONE) | EPI_DIRECT>(h, c, st);
       case epi_code(false, true, false, false, ACT_QUICKGELU): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU)>(h, c, st);
-      case epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU) | EPI_DIRECT>(h, c, st);
       case epi_code(false, true, false, false, ACT_GELU_ERF): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF)>(h, c, st);
-      case epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_DIRECT>(h, c, st);
       default: break;
     }
   }
@@ -389,8 +352,8 @@ static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st)
       default: break;
     }
   }
-  return fail(h, "gemm: epilogue combination not instantiated (transposed=%d bf16=%d resid=%d atomic=%d act=%d bn=%d)",
-              p.transposed, p.out_bf16, p.resid != nullptr, p.atomic, p.act, BN);
+  return fail(h, "gemm: epilogue combination not instantiated (transposed=%d bf16=%d resid=%d partial=%d act=%d bn=%d)",
+              p.transposed, p.out_bf16, p.resid != nullptr, p.partial, p.act, BN);
 }
 
 static int pick_bn(const gitb200_engine* h, int M, int N, bool transposed) {
@@ -422,8 +385,9 @@ static int launch_gemm(gitb200_engine* h, GemmCall c, cudaStream_t st) {
   }
   if (!p.transposed && (p.N % 32 != 0 || p.seg_n % 32 != 0))
     return fail(h, "gemm: N and segment width must be multiples of 32 (N=%d seg=%d)", p.N, p.seg_n);
-  if (p.atomic && !p.transposed) return fail(h, "gemm: atomic accumulation is only implemented for the transposed epilogue");
-  if (p.k_splits > 1 && !p.atomic) return fail(h, "gemm: k_splits > 1 needs the atomic epilogue");
+  if (p.partial && !p.transposed) return fail(h, "gemm: split-K partial buffers are only implemented for the transposed epilogue");
+  if (p.k_splits > 1 && !p.partial) return fail(h, "gemm: k_splits > 1 needs the partial-sum epilogue");
+  if (p.partial && p.split_stride < static_cast<long long>(p.N) * p.ldo) return fail(h, "gemm: split_stride smaller than one partial buffer");
   int bn = c.bn > 0 ? c.bn : pick_bn(h, p.M, p.N, p.transposed != 0);
   // 2-CTA (cta_group::2) kernel: explicit request (bn = 1000 + BN, unit tests) or engine option for the big GEMMs
   // Measured (tools/gemm_sweep.py, M = 12608): pairs win on wide outputs (+7-10 %) and on K = 3072 (+11 %); the
@@ -449,24 +413,6 @@ static int launch_gemm(gitb200_engine* h, GemmCall c, cudaStream_t st) {
   }
 }
 
-static int launch_skinny(gitb200_engine* h, const SkinnyParams& p, cudaStream_t st) {
-  if (p.R > kSkinnyRows) return fail(h, "skinny gemm: at most %d rows (got %d)", kSkinnyRows, p.R);
-  if (p.KS % 128 != 0 || p.K % p.KS != 0 || p.N % 8 != 0 || p.K % 8 != 0)
-    return fail(h, "skinny gemm: unsupported shape N=%d K=%d KS=%d", p.N, p.K, p.KS);
-  const size_t smem = skinny_smem_bytes(p.KS);
-  if (smem > 227 * 1024) return fail(h, "skinny gemm: k-depth %d does not fit in shared memory", p.KS);
-  static size_t attr_done[64] = {0};
-  if (attr_done[h->device & 63] < smem) {
-    CK(cudaFuncSetAttribute(skinny_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done[h->device & 63] = smem;
-  }
-  dim3 grid((p.N + kSkinnyFT - 1) / kSkinnyFT, p.K / p.KS);
-  h->last_gemm_grid = static_cast<int>(grid.x * grid.y);
-  CK(launch_k(p.pdl != 0, skinny_mma_kernel, grid, dim3(256), smem, st, p));
-  CKL(h, "skinny_mma_kernel");
-  return 0;
-}
-
 // Plain C = A W^T (+bias)(+act)(+resid) -> out (fp32 or bf16), identity row map.
 static GemmCall gemm_plain(const bf16* A, long long lda, const bf16* W, long long ldw, int M, int N, int K,
                            const float* bias, int act, const float* resid, void* out, bool out_bf16) {
@@ -479,13 +425,15 @@ static GemmCall gemm_plain(const bf16* A, long long lda, const bf16* W, long lon
   return c;
 }
 // Skinny decode-step GEMM: out[r][f] = sum_k X[r][k] W[f][k] (+bias[f]) (+act) -- swap-AB, transposed epilogue.
+// k_splits > 1: split s writes its partial sums to out + s * rows * ldo (fp32); the consumer adds them in split order.
 static GemmCall gemm_skinny(const bf16* X, long long ldx, const bf16* W, long long ldw, int rows, int feats, int K,
                             const float* bias, int act, void* out, long long ldo, bool out_bf16, int k_splits,
                             const int* skip, bool pdl = false) {
   GemmCall c;
   c.A = W; c.lda = ldw; c.B = X; c.ldb = ldx;
   c.p.M = feats; c.p.N = rows; c.p.K = K; c.p.k_splits = k_splits;
-  c.p.transposed = 1; c.p.atomic = k_splits > 1 ? 1 : 0;
+  c.p.transposed = 1; c.p.partial = k_splits > 1 ? 1 : 0;
+  c.p.split_stride = static_cast<long long>(rows) * ldo;
   c.p.bias = bias; c.p.act = act;
   c.p.out[0] = out; c.p.ldo = ldo; c.p.out_bf16 = out_bf16 ? 1 : 0;
   c.p.skip = skip;
@@ -549,9 +497,14 @@ __global__ void cvt_rows_kernel(const float* __restrict__ src, long long src_ld,
     dst[r * dst_ld + c] = __float2bfloat16_rn(c < cols ? src[r * src_ld + c] : 0.0f);
   }
 }
-__global__ void set_state_kernel(StepState* states, int pos, int cur_len, unsigned int* chains) {
-  StepState* st = states + blockIdx.x;
-  unsigned int* chain = chains + blockIdx.x * 64;
+__global__ void sum_partials_kernel(const float* __restrict__ parts, float* __restrict__ out, long long n, int splits) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a = parts[i];
+    for (int s = 1; s < splits; ++s) a += parts[s * n + i];
+    out[i] = a;
+  }
+}
+__global__ void set_state_kernel(StepState* st, int pos, int cur_len, unsigned int* chain) {
   st->pos = pos; st->cur_len = cur_len; st->finished = 0; st->final_len = cur_len; st->step = 0;
   st->empty_caption = 0; st->ticket = 0; st->not_eos = 0;
   for (int k = 0; k < 64; ++k) chain[k] = 0;
@@ -585,24 +538,10 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (!h || !name) return 1;
   // the captured decode-step graph bakes the launch configuration in: drop it whenever an option changes
   drop_step_graphs(h);
-  if (strcmp(name, "pdl_late") == 0) {   // process-wide (a __constant__ the chain kernels read)
-    const int v = value != 0 ? 1 : 0;
-    cudaSetDevice(h->device);
-    CK(cudaMemcpyToSymbol(g_pdl_late, &v, sizeof(int)));
-    return 0;
-  }
-  if (strcmp(name, "prio_split") == 0) { h->prio_split = value != 0; return 0; }
-  if (strcmp(name, "attn_pipe") == 0) { h->attn_pipe = value != 0; return 0; }
-  if (strcmp(name, "kv_head_major") == 0) { h->kv_head_major = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
-  if (strcmp(name, "use_lean") == 0) { h->use_lean = value != 0; return 0; }
-  if (strcmp(name, "decode_ctas") == 0) { h->decode_ctas = value < 0 ? 0 : static_cast<int>(value); return 0; }
-  if (strcmp(name, "sm_reserve") == 0) { h->sm_reserve = value < 0 ? 0 : (value > 64 ? 64 : static_cast<int>(value)); return 0; }
   if (strcmp(name, "use_2cta") == 0) { h->use_2cta = value != 0; return 0; }
-  if (strcmp(name, "epi_direct") == 0) { h->epi_direct = value != 0; return 0; }
-  if (strcmp(name, "lanes") == 0) { h->lanes_opt = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : static_cast<int>(value)); return 0; }
   return fail(h, "unknown option %s", name);
 }
 
@@ -663,7 +602,7 @@ static void release_all(gitb200_engine* h) {
   DevBuf* bufs[] = {&h->w_patch, &h->cls, &h->pos_emb, &h->lnpre_g, &h->lnpre_b, &h->lnpost_g, &h->lnpost_b, &h->w_vp,
                     &h->b_vp, &h->lnvp_g, &h->lnvp_b, &h->words_f32, &h->words_bf16, &h->positions, &h->lnemb_g,
                     &h->lnemb_b, &h->out_bias, &h->temb, &h->x, &h->h, &h->qkv, &h->ctx, &h->u, &h->feats, &h->feats_f32, &h->pos_interp,
-                    &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->img_kv_hm, &h->txt_kv, &h->src_row[0],
+                    &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->txt_kv, &h->src_row[0],
                     &h->src_row[1], &h->xd_t, &h->hd_t, &h->qkv_t, &h->ctx_t, &h->t_t, &h->u_t, &h->logits, &h->state,
                     &h->next_token, &h->logprob_sum, &h->tokens_i64, &h->stage_img, &h->stage_tok, &h->stage_lp,
                     &h->prefix_dev, &h->beam_ws, &h->sel_ws, &h->chain};
@@ -713,13 +652,10 @@ extern "C" void gitb200_destroy(gitb200_engine* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   drop_step_graphs(h);
-  for (int i = 0; i < kMaxLanes; ++i) { if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->host_state) cudaFreeHost(h->host_state);
   if (h->own_event) cudaEventDestroy(h->own_event);
+  for (int i = 0; i < 2; ++i) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
-  if (h->prio_stream) cudaStreamDestroy(h->prio_stream);
-  for (int i = 0; i < 2; ++i) if (h->prio_ev[i]) cudaEventDestroy(h->prio_ev[i]);
   release_all(h);
   delete h;
 }
@@ -972,6 +908,11 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
 // ------------------------------------------------------------------------------------------------
 // hot path B: prefill (image rows of the decoder, computed once) + decode step
 // ------------------------------------------------------------------------------------------------
+// Split-K factors of the decode-step GEMMs: a handful of activation rows against [features, K] weights is latency
+// bound, so K is spread over enough CTAs that each one has all of its weight tiles in flight at once.  Every split
+// stores its own partial-sum buffer; the consumer (decode attention / LayerNorm) adds them in split order.
+constexpr int kQkvSplits = 3, kOutProjSplits = 6, kFc2Splits = 8, kMaxProjSplits = 8;
+
 static bf16* img_kv_ptr(gitb200_engine* h, int layer, int kv) {
   const long long per = static_cast<long long>(h->cur_B) * h->cur_M * h->D;
   return h->img_kv.as<bf16>() + (static_cast<long long>(layer) * 2 + kv) * per;
@@ -998,12 +939,12 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
   CK(h->src_row[1].ensure(static_cast<size_t>(R) * T_alloc * 4));
   CK(h->xd_t.ensure(static_cast<size_t>(R) * D * 4));
   CK(h->hd_t.ensure(static_cast<size_t>(R) * D * 2));
-  CK(h->qkv_t.ensure(static_cast<size_t>(R) * 3 * D * 4));
+  CK(h->qkv_t.ensure(static_cast<size_t>(kQkvSplits) * R * 3 * D * 4));   // split-K partial-sum buffers
   CK(h->ctx_t.ensure(static_cast<size_t>(R) * D * 2));
-  CK(h->t_t.ensure(static_cast<size_t>(R) * D * 4));
+  CK(h->t_t.ensure(static_cast<size_t>(kMaxProjSplits) * R * D * 4));
   CK(h->u_t.ensure(static_cast<size_t>(R) * F * 2));
   CK(h->logits.ensure(static_cast<size_t>(R) * h->V * 4));
-  CK(h->state.ensure(sizeof(StepState) * kMaxLanes));
+  CK(h->state.ensure(sizeof(StepState)));
   CK(h->next_token.ensure(static_cast<size_t>(R) * 8));
   CK(h->logprob_sum.ensure(static_cast<size_t>(R) * 4));
   h->cur_beam = beam;
@@ -1015,9 +956,6 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
   bf16* q = h->pq.as<bf16>();
   bf16* ctx = h->pctx.as<bf16>();
   bf16* u = h->pu.as<bf16>();
-  // split-K accumulation buffer of the decode step must start at zero
-  CK(cudaMemsetAsync(h->t_t.p, 0, static_cast<size_t>(R) * D * 4, st));
-  CK(cudaMemsetAsync(h->qkv_t.p, 0, static_cast<size_t>(R) * 3 * D * 4, st));
 
   // visual projection: Linear(dv -> 768) + LayerNorm(1e-5)
   TRY(launch_gemm(h, gemm_plain(h->feats.as<bf16>(), d, h->w_vp.as<bf16>(), d, static_cast<int>(rows), D, d, h->b_vp.as<float>(), ACT_NONE, nullptr, t, false), st));
@@ -1046,14 +984,6 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
     TRY(launch_gemm(h, gemm_plain(u, F, l.w2.as<bf16>(), F, static_cast<int>(rows), D, F, l.b2.as<float>(), ACT_NONE, xd, t, false), st));
     TRY(launch_ln(h, ln_params(t, nullptr, nullptr, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, static_cast<int>(rows)), D, st));
   }
-  if (h->kv_head_major) {
-    const long long n_img = static_cast<long long>(nl) * 2 * B;
-    CK(h->img_kv_hm.ensure(static_cast<size_t>(n_img) * M * D * 2));
-    const long long units = n_img * M * (D / 8);
-    const int grid = static_cast<int>(std::min<long long>((units + 255) / 256, h->num_sms * 32));
-    kv_head_major_kernel<<<grid, 256, 0, st>>>(h->img_kv.as<bf16>(), h->img_kv_hm.as<bf16>(), n_img, M, H);
-    CKL(h, "kv_head_major_kernel");
-  }
   return 0;
 }
 
@@ -1063,7 +993,7 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
 static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, const int* src_row, bool lm_head) {
   const int D = h->D, F = h->F, R = ln_.rows, nl = h->cfg.dec_layers, beam = h->cur_beam;
   cudaStream_t st = ln_.st;
-  StepState* state = h->state.as<StepState>() + ln_.idx;
+  StepState* state = h->state.as<StepState>();
   const int* skip = &state->finished;
   const long long r0 = ln_.row0;
   float* xd = h->xd_t.as<float>() + r0 * D;
@@ -1079,7 +1009,7 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
   // Ordering inside the step: flag chain (greedy; the beam bookkeeping kernels still use grid dependencies).
   const bool chain_on = pdl && h->use_chain && beam == 1;
   ChainSync cs{};
-  cs.counters = chain_on ? h->chain.as<unsigned int>() + ln_.idx * 64 : nullptr;
+  cs.counters = chain_on ? h->chain.as<unsigned int>() : nullptr;
   cs.idx = 0;
   cs.pred_ctas = 0;
   auto next_link = [&](unsigned int ctas_of_this_kernel) {  // call after each launch
@@ -1092,74 +1022,52 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
               static_cast<const StepState*>(state), h->V, cs));
   CKL(h, "embed_ln_kernel");
   next_link((R + 7) / 8);
-  // Split-K factors: a handful of activation rows against [features, K] weights is latency bound, so the K
-  // dimension is spread over enough CTAs that each one has all of its weight tiles in flight at once
-  // (partials meet in fp32 atomics; bias / residual / LayerNorm live in the consumer kernel).
+  // split-K GEMMs write partial-sum buffers; bias / residual / LayerNorm live in the consumer kernel
   auto skinny = [&](GemmCall c) -> int {
     c.p.chain = cs;
     TRY(launch_gemm(h, c, st));
     next_link(static_cast<unsigned int>(h->last_gemm_grid));
     return 0;
   };
+  auto ln_partials = [&](const float* parts, int n, int rows, const float* bias, const float* resid, const float* g,
+                         const float* b, float* of32, bf16* obf16) {
+    LnParams p = ln_params(parts, bias, resid, g, b, 1e-12f, of32, obf16, rows);
+    p.n_partials = n;
+    p.partial_stride = static_cast<long long>(rows) * D;
+    return p;
+  };
   auto ln = [&](LnParams p) -> int {
-    p.zero_x = 1; p.skip_flag = skip; p.chain = cs;
+    p.skip_flag = skip; p.chain = cs;
     TRY(launch_ln(h, p, D, st, pdl));
     next_link((p.rows + 7) / 8);
     return 0;
   };
-  const bool lean = h->use_lean && R <= kSkinnyRows;
-  auto lean_gemm = [&](const bf16* X, long long ldx, const bf16* W, int N, int K, int KS, const float* bias, int act, int mode,
-                       void* out, long long ldo) -> int {
-    SkinnyParams sp{};
-    sp.X = X; sp.ldx = ldx; sp.W = W; sp.ldw = K; sp.R = R; sp.N = N; sp.K = K; sp.KS = KS;
-    sp.bias = bias; sp.act = act; sp.mode = mode; sp.out = out; sp.ldo = ldo;
-    sp.skip = skip; sp.pdl = pdl ? 1 : 0; sp.chain = cs;
-    TRY(launch_skinny(h, sp, st));
-    next_link(static_cast<unsigned int>(h->last_gemm_grid));
-    return 0;
-  };
   for (int j = 0; j < nl; ++j) {
     DecLayer& l = h->dec[j];
-    if (lean) TRY(lean_gemm(hd, D, l.wqkv.as<bf16>(), 3 * D, D, D, l.bqkv.as<float>(), ACT_NONE, 0, qkv, 3 * D));
-    else TRY(skinny(gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, nullptr, ACT_NONE, qkv, 3 * D, false, 3, skip, pdl)));
+    TRY(skinny(gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, nullptr, ACT_NONE, qkv, 3 * D, false, kQkvSplits, skip, pdl)));
     DecAttnParams ap{};
-    ap.qkv = qkv; ap.bqkv = lean ? nullptr : l.bqkv.as<float>();   // lean QKV: bias already added, plain stores (no re-zeroing)
+    ap.qkv = qkv; ap.n_partials = kQkvSplits; ap.partial_stride = static_cast<long long>(R) * 3 * D;
+    ap.bqkv = l.bqkv.as<float>();
     ap.img_k = img_kv_ptr(h, j, 0) + img_off; ap.img_v = img_kv_ptr(h, j, 1) + img_off;
-    ap.head_major = h->kv_head_major ? 1 : 0;
-    if (h->kv_head_major) {   // same offsets inside the head-major copy (an image still owns M * D elements)
-      const long long delta = h->img_kv_hm.as<bf16>() - h->img_kv.as<bf16>();
-      ap.img_k += delta;
-      ap.img_v += delta;
-    }
     ap.txt_k = txt_kv_ptr(h, j, 0) + txt_off; ap.txt_v = txt_kv_ptr(h, j, 1) + txt_off;
     ap.src_row = src_row; ap.ctx = ctx; ap.B = ln_.nb; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
     ap.state = state;
     ap.chunk_rows = h->attn_chunk_rows; ap.box_rows = h->attn_box_rows;
     ap.chain = cs;
     CUtensorMap tk, tv;
-    if (h->kv_head_major) {
-      const long long hm_rows = static_cast<long long>(ln_.nb) * h->cfg.dec_heads * h->cur_M;
-      TRY(get_tmap(h, ap.img_k, hm_rows, 64, 64, ap.box_rows, &tk, false));
-      TRY(get_tmap(h, ap.img_v, hm_rows, 64, 64, ap.box_rows, &tv, false));
-    } else {
-      TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
-      TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
-    }
-    dim3 grid(std::min(h->decode_ctas > 0 ? std::min(h->attn_grid, h->decode_ctas) : h->attn_grid, ln_.nb * h->cfg.dec_heads));
-    if (beam == 1 && h->attn_pipe) CK(launch_k(pdl, decode_attn_kernel<1, true>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
-    else if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+    TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
+    TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
+    dim3 grid(std::min(h->attn_grid, ln_.nb * h->cfg.dec_heads));
+    if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1, true>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
     else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
     CKL(h, "decode_attn_kernel");
     next_link(grid.x);
-    if (lean) TRY(lean_gemm(ctx, D, l.wo.as<bf16>(), D, D, D, nullptr, ACT_NONE, 0, t, D));
-    else TRY(skinny(gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, 6, skip, pdl)));
-    TRY(ln(ln_params(t, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, R)));
-    if (lean) TRY(lean_gemm(hd, D, l.w1.as<bf16>(), F, D, D, l.b1.as<float>(), ACT_GELU_ERF, 1, u, F));
-    else TRY(skinny(gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip, pdl)));
-    if (lean) TRY(lean_gemm(u, F, l.w2.as<bf16>(), D, F, 768, nullptr, ACT_NONE, 2, t, D));
-    else TRY(skinny(gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, 12, skip, pdl)));
-    TRY(ln(ln_params(t, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, R)));
+    TRY(skinny(gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, kOutProjSplits, skip, pdl)));
+    TRY(ln(ln_partials(t, kOutProjSplits, R, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), xd, hd)));
+    TRY(skinny(gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip, pdl)));
+    TRY(skinny(gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, kFc2Splits, skip, pdl)));
+    TRY(ln(ln_partials(t, kFc2Splits, R, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), xd, hd)));
   }
   if (lm_head)
     TRY(skinny(gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, logits, h->V, false, 1, skip, pdl)));
@@ -1181,11 +1089,10 @@ static int set_attn_smem_limit(gitb200_engine* h) {
   const int per_sm = (h->attn_smem * 2 + 8 * 1024 <= 227 * 1024) ? 2 : 1;
   const int items = h->cur_B * h->cfg.dec_heads;
   h->attn_grid = std::min(items, per_sm * h->num_sms);
-  CK(cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(cudaFuncSetAttribute(decode_attn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
-  CK(h->chain.ensure(256 * kMaxLanes));
-  CK(cudaMemset(h->chain.p, 0, 256 * kMaxLanes));
+  CK(h->chain.ensure(256));
+  CK(cudaMemset(h->chain.p, 0, 256));
   return 0;
 }
 

@@ -180,104 +180,4 @@ pre_vertical_norm_kernel(const uint8_t* __restrict__ tmp, float* __restrict__ ou
 }
 
 
-// ---- second-generation kernels: same arithmetic, fewer load instructions --------------------------------------------
-// (the first-generation kernels are LSU bound: 33 byte loads + 11 lane-strided weight loads per output pixel)
-//
-// Pass 1, v2: the taps of one output pixel are 3 * cnt contiguous bytes at an arbitrary offset; they are fetched as aligned
-// 32-bit words and unpacked with shifts (needs a 4-byte aligned source buffer whose size is a multiple of 4); the weight
-// table is stored tap-major ([kh][out_w]) so that the 32 lanes of a warp (32 neighbouring x) read 32 neighbouring weights.
-__global__ void __launch_bounds__(256)
-pre_horizontal_kernel_v2(const uint8_t* __restrict__ src, uint8_t* __restrict__ tmp, const PreImage* __restrict__ imgs,
-                         const int32_t* __restrict__ tab) {
-  const PreImage im = imgs[blockIdx.y];
-  const long long total = static_cast<long long>(im.rows) * im.out_w;
-  uint8_t* t0 = tmp + im.tmp_off;
-  const int32_t* hb = tab + im.hb_off;
-  const int32_t* hk = tab + im.hk_off;    // [kh][out_w]
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / im.out_w);
-    const int x = static_cast<int>(i - static_cast<long long>(r) * im.out_w);
-    const int lo = __ldg(hb + 2 * x), cnt = __ldg(hb + 2 * x + 1);
-    const long long addr = im.src_off + (static_cast<long long>(im.row0 + r) * im.src_w + lo) * 3;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + (addr & ~3LL));
-    int sh = static_cast<int>(addr & 3) * 8;
-    int left = cnt * 3;
-    uint32_t cur = __ldg(wp);
-    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-    const int32_t* k = hk + x;
-    for (int j = 0; j < cnt; ++j) {
-      const int w = __ldg(k);
-      k += im.out_w;
-      int v[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        v[c] = static_cast<int>((cur >> sh) & 0xffu);
-        sh += 8;
-        --left;
-        if (sh == 32 && left > 0) { cur = __ldg(++wp); sh = 0; }
-      }
-      a0 += v[0] * w;
-      a1 += v[1] * w;
-      a2 += v[2] * w;
-    }
-    uint8_t* o = t0 + i * 3;
-    o[0] = static_cast<uint8_t>(min(max(a0 >> kPrecisionBits, 0), 255));
-    o[1] = static_cast<uint8_t>(min(max(a1 >> kPrecisionBits, 0), 255));
-    o[2] = static_cast<uint8_t>(min(max(a2 >> kPrecisionBits, 0), 255));
-  }
-}
-
-// Pass 2, v2: the vertical pass does not care which channel a byte belongs to, so a thread takes 4 consecutive bytes of
-// an intermediate row (one 32-bit load per tap instead of 12 byte loads per 4 values; needs out_w % 4 == 0 so that every
-// row starts 4-byte aligned), normalises them into a shared-memory row [3][out_w] and the block then writes the three
-// planes with fully coalesced stores. One block iteration = one output row.
-__global__ void __launch_bounds__(256)
-pre_vertical_norm_kernel_v2(const uint8_t* __restrict__ tmp, float* __restrict__ out, const PreImage* __restrict__ imgs,
-                            const int32_t* __restrict__ tab, float m0, float m1, float m2, float s0, float s1, float s2) {
-  extern __shared__ float pre_row[];      // [3][out_w]
-  const PreImage im = imgs[blockIdx.y];
-  const long long plane = static_cast<long long>(im.out_h) * im.out_w;
-  const uint8_t* t0 = tmp + im.tmp_off;
-  float* o = out + im.dst_off;
-  const int32_t* vb = tab + im.vb_off;
-  const int32_t* vk = tab + im.vk_off;
-  const int rb = im.out_w * 3;            // bytes per intermediate row (multiple of 4)
-  const int quads = rb >> 2;
-  for (int y = blockIdx.x; y < im.out_h; y += gridDim.x) {
-    const int lo = __ldg(vb + 2 * y), cnt = __ldg(vb + 2 * y + 1);
-    const int32_t* k = vk + static_cast<long long>(y) * im.kv;
-    for (int q = threadIdx.x; q < quads; q += blockDim.x) {
-      const uint8_t* p = t0 + static_cast<long long>(lo) * rb + 4 * q;
-      int a[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = 1 << (kPrecisionBits - 1);
-      for (int j = 0; j < cnt; ++j) {
-        const int w = __ldg(k + j);
-        const uint32_t word = *reinterpret_cast<const uint32_t*>(p);
-        p += rb;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] += static_cast<int>((word >> (8 * i)) & 0xffu) * w;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int flat = 4 * q + i;
-        const int x = flat / 3;
-        const int c = flat - 3 * x;
-        const float v = static_cast<float>(min(max(a[i] >> kPrecisionBits, 0), 255));
-        const float m = c == 0 ? m0 : (c == 1 ? m1 : m2);
-        const float s = c == 0 ? s0 : (c == 1 ? s1 : s2);
-        pre_row[c * im.out_w + x] = __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), m), s);
-      }
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < rb; idx += blockDim.x) {
-      const int c = idx / im.out_w;
-      const int x = idx - c * im.out_w;
-      o[c * plane + static_cast<long long>(y) * im.out_w + x] = pre_row[idx];
-    }
-    __syncthreads();
-  }
-}
-
 }  // namespace gitb200

@@ -20,23 +20,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Optional in-situ timeline (debug): when enabled, block 0 / thread 0 of every decode-step kernel appends
-// (%globaltimer, kernel id) right after its dependency wait, i.e. when its predecessor has fully completed.
+// Optional in-situ timeline (debug builds only: nvcc -DGITB200_TIMELINE, see build.py / tools/step_timeline2.py): block 0 /
+// thread 0 of every decode-step kernel appends (%globaltimer, kernel id) at its start, right after its dependency wait
+// (i.e. when its predecessor has fully completed) and at its end.  The production library contains none of this.
+#ifdef GITB200_TIMELINE
 __device__ unsigned long long* g_tl_buf = nullptr;
 __device__ unsigned int g_tl_count = 0;
 constexpr unsigned int kTimelineMax = 8192;
-__device__ __forceinline__ void tl_mark(int kid) {
-  if (g_tl_buf != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    const unsigned int i = atomicAdd(&g_tl_count, 1u);
-    if (i < kTimelineMax) {
-      g_tl_buf[2 * i] = globaltimer_ns();
-      g_tl_buf[2 * i + 1] = static_cast<unsigned long long>(kid);
-    }
-  }
-}
-
-// same, for one designated thread of block 0 that is not thread 0
-__device__ __forceinline__ void tl_mark_one(int kid) {
+__device__ __forceinline__ void tl_mark_one(int kid) {   // one designated thread of block 0
   if (g_tl_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
     const unsigned int i = atomicAdd(&g_tl_count, 1u);
     if (i < kTimelineMax) {
@@ -45,19 +36,22 @@ __device__ __forceinline__ void tl_mark_one(int kid) {
     }
   }
 }
+__device__ __forceinline__ void tl_mark(int kid) {
+  if (threadIdx.x == 0) tl_mark_one(kid);
+}
+#else
+__device__ __forceinline__ void tl_mark(int) {}
+__device__ __forceinline__ void tl_mark_one(int) {}
+#endif
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
 // start while its predecessor is still running; griddep_wait() blocks until the predecessor grid has completed
 // and its writes are visible, griddep_launch() lets the successor's prologue begin. Both are no-ops otherwise.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-// Where a decode-chain kernel releases its PDL successor.  Early (0, at kernel entry): the successor's prologue and
-// weight prefetch overlap as much as possible, but every kernel of the chain that fits becomes resident and spins,
-// which starves the chains of OTHER batches in flight.  Late (1, once this kernel's own dependency is satisfied):
-// at most one waiting successor per chain is resident.
-__constant__ int g_pdl_late = 0;
-__device__ __forceinline__ void griddep_launch_early() { if (g_pdl_late == 0) griddep_launch(); }
-__device__ __forceinline__ void griddep_launch_late() { if (g_pdl_late != 0) griddep_launch(); }
+// The decode-chain kernels release their PDL successor at kernel entry: its prologue and weight prefetch overlap as much
+// as possible (a late release, once the kernel's own dependency is satisfied, was measured in round 1: no gain).
+__device__ __forceinline__ void griddep_launch_early() { griddep_launch(); }
 
 // Flag-based ordering of the decode-step kernel chain.  Kernel k of a step (launched with the PDL attribute, so
 // it may become resident while kernel k-1 still runs, but WITHOUT griddepcontrol.wait) spins until every CTA of

@@ -29,7 +29,8 @@ struct LnParams {
   float* out_f32;        // may alias x (in place) or be null
   __nv_bfloat16* out_bf16;  // or null
   int rows;
-  int zero_x;            // write zeros back to x after reading (split-K accumulation buffers)
+  int n_partials;        // > 1: x is the first of n split-K partial-sum buffers, partial_stride elements apart; they are
+  long long partial_stride;  // added in split order (fixed order -> bit-reproducible; nothing to re-zero)
   // optional frame remap (video path, reference layers/decoder.py:846-851): input row (f*B + b)*L + l ->
   // output row b*(F*L) + f*L + l, plus `+ temb[f]` AFTER the normalisation.
   const float* temb;     // [F, D] or null
@@ -65,7 +66,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     griddep_wait();
     if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
   }
-  griddep_launch_late();
   tl_mark(2);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= p.rows) {
@@ -76,6 +76,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const float4* xp = reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * D);
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = __ldcg(xp + i * 32 + lane);
+  for (int s0 = 1; s0 < p.n_partials; s0 += 3) {   // three partial buffers per round trip, added in split order
+    float4 w[3][NV];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const bool ok = s0 + k < p.n_partials;
+      const float4* sp = reinterpret_cast<const float4*>(p.x + (ok ? s0 + k : 0) * p.partial_stride + static_cast<long long>(row) * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) w[k][i] = ok ? __ldcg(sp + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { v[i].x += w[k][i].x; v[i].y += w[k][i].y; v[i].z += w[k][i].z; v[i].w += w[k][i].w; }
+    }
+  }
   if (p.resid != nullptr) {
     const float4* rp = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * D);
 #pragma unroll
@@ -83,11 +98,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       const float4 r = __ldcg(rp + i * 32 + lane);
       v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
     }
-  }
-  if (p.zero_x) {
-    float4* zp = reinterpret_cast<float4*>(const_cast<float*>(p.x) + static_cast<long long>(row) * D);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) zp[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (PRE) {
 #pragma unroll
@@ -373,7 +383,6 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
     griddep_wait();
     if (st->finished) return;
   }
-  griddep_launch_late();
   tl_mark(5);
   const int row = blockIdx.y;
   const int split = blockIdx.x;
@@ -504,25 +513,13 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
   }
 }
 
-// logprobs / num_valid (reference layers/decoder.py:433-438) and EOS padding of the unused tail.  With decode lanes
-// the loop length is that of the slowest lane (the reference stops when ALL rows have ended; rows of a lane that
-// stopped earlier would only have been fed forced EOS steps, which add exactly 0 to their logprob).
-struct LaneRows {
-  int n;
-  int row0[4];
-  int rows[4];
-};
+// logprobs / num_valid (reference layers/decoder.py:433-438) and EOS padding of the unused tail.
 __global__ void greedy_finalize_kernel(long long* tokens_out, const float* logprob_sum, float* logprobs_out, int rows,
-                                       int max_steps, int prefix_len, int eos, StepState* states, LaneRows lanes) {
+                                       int max_steps, int prefix_len, int eos, const StepState* state) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
-  int n = 0, empty = 1, n_lane = 0;
-  for (int l = 0; l < lanes.n; ++l) {
-    n = max(n, states[l].final_len);
-    empty &= states[l].empty_caption;
-    if (row >= lanes.row0[l] && row < lanes.row0[l] + lanes.rows[l]) n_lane = states[l].final_len;
-  }
-  for (int i = n_lane; i < max_steps; ++i) tokens_out[static_cast<long long>(row) * max_steps + i] = eos;
+  const int n = state->final_len;
+  for (int i = n; i < max_steps; ++i) tokens_out[static_cast<long long>(row) * max_steps + i] = eos;
   int not_eos = 0, has_eos = 0;
   for (int i = 0; i < n; ++i) {
     const long long t = tokens_out[static_cast<long long>(row) * max_steps + i];
@@ -530,7 +527,7 @@ __global__ void greedy_finalize_kernel(long long* tokens_out, const float* logpr
   }
   int num_valid = not_eos + has_eos - prefix_len;
   if (num_valid < 1) num_valid = 1;
-  logprobs_out[row] = empty ? logprob_sum[row] : logprob_sum[row] / static_cast<float>(num_valid);
+  logprobs_out[row] = state->empty_caption ? logprob_sum[row] : logprob_sum[row] / static_cast<float>(num_valid);
 }
 
 }  // namespace gitb200

@@ -236,10 +236,12 @@ __global__ void __launch_bounds__(32) beam_update_kernel(const BeamParams p) {
   // loop-state advance by the last image
   __threadfence();
   if (lane == 0) {
-    const unsigned int t = atomicAdd(&st->ticket, 1u);
+    // count this image as running BEFORE drawing the ticket: the block that draws the last ticket then sees every add
     if (p.s.done[b] == 0) atomicAdd(&st->not_eos, 1);  // re-used as "images still running"
     __threadfence();
+    const unsigned int t = atomicAdd(&st->ticket, 1u);
     if (t == static_cast<unsigned int>(p.B) - 1) {
+      __threadfence();
       const int running = atomicAdd(&st->not_eos, 0);
       st->ticket = 0;
       st->not_eos = 0;

@@ -59,11 +59,22 @@ def load_from_yaml_file(file_name):
     import yaml
     with open(file_name, 'r') as fp:
         data = yaml.safe_load(fp)
-    while isinstance(data, dict) and '_base_' in data:       # reference tsv_io.py:103-119
+    while isinstance(data, dict) and '_base_' in data:       # reference tsv_io.py:97-107: per-path merge into the base
         base = load_from_yaml_file(op.join(op.dirname(file_name), data.pop('_base_')))
-        base.update(data)
+        assert isinstance(base, dict)
+        _merge_paths(base, data)
         data = base
     return data or {}
+
+
+def _merge_paths(base, child):
+    """Every leaf path of `child` overrides the same path of `base` (nested dicts are merged, not replaced; lists and
+    scalars are leaves) -- what the reference's get_all_path / dict_update_path_value loop does (tsv_io.py:102-106)."""
+    for k, v in child.items():
+        if isinstance(v, dict) and isinstance(base.get(k), dict):
+            _merge_paths(base[k], v)
+        else:
+            base[k] = v
 
 
 class MinMaxResizeForTest(object):
@@ -106,12 +117,12 @@ class ImageTransform(object):
     """`get_image_transform(param)`: callable on one decoded image like the reference's `Compose`, but the result is a
     CUDA tensor (the reference's callers do `.cuda()` next, a no-op then); `batch()` transforms many images per call."""
 
-    def __init__(self, param, device=None, fast=None):
+    def __init__(self, param, device=None):
         param = param or {}
-        self.fast = bool(int(os.environ.get('GITB200_PREPROC_FAST', '0'))) if fast is None else bool(fast)
         self.crop_size = param.get('test_crop_size', 224)
         self.respect_ratio_max = param.get('test_respect_ratio_max')
-        self.minmax = MinMaxResizeForTest(self.crop_size, self.respect_ratio_max) if self.respect_ratio_max else None
+        # the reference tests `'test_respect_ratio_max' in param` (inference.py:113), not the value's truthiness
+        self.minmax = MinMaxResizeForTest(self.crop_size, self.respect_ratio_max) if 'test_respect_ratio_max' in param else None
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None and torch.cuda.is_available() \
             else (torch.device(device) if device is not None else None)
         self._handle = None
@@ -145,7 +156,6 @@ class ImageTransform(object):
             if lib.gitb200_preproc_create(self.device.index or 0, ctypes.byref(h)) != 0:
                 raise RuntimeError('gitb200_preproc_create failed: %s' % (lib.gitb200_preproc_last_error(None) or b'').decode())
             self._handle = h
-            lib.gitb200_preproc_set_option(h, b'fast', int(self.fast))
         return _lib.load()
 
     def batch(self, imgs):
@@ -203,9 +213,9 @@ class ImageTransform(object):
             pass
 
 
-def get_image_transform(param, device=None, fast=None):
+def get_image_transform(param, device=None):
     """reference inference.py:111-132."""
-    return ImageTransform(param, device, fast)
+    return ImageTransform(param, device)
 
 
 def _default_tokenizer():
@@ -336,7 +346,10 @@ def test_git_inference_single_tsv(image_tsv, model_name, question_tsv, out_tsv, 
 
     def decode_row(i):
         key, col = image_tsv[i][:2]
-        return key, pilimg_from_base64(col)
+        img = pilimg_from_base64(col)
+        if img is None:     # the reference crashes inside its transform on such a row (inference.py:204); name the row
+            raise ValueError('row %d (key %r) of the image tsv does not decode to an image' % (i, key))
+        return key, img
 
     def caption_rows():
         """Batches of decoded rows -> GPU transform -> model.submit with `depth` batches in flight."""

@@ -216,13 +216,26 @@ class GitB200CaptioningModel(nn.Module):
         self._engine_device = None
         self._next_slot = 0
         self._open_group = None      # batches waiting to be launched together (submit(..., coalesce=k))
+        self._param_cache = None
 
     # ---------------------------------------------------------------- engine plumbing
     def _device(self):
         return self.textual.embedding.words.weight.device
 
     def _weights_signature(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        # (storage address, in-place version) of every parameter; the (name, tensor) list itself is cached and dropped by
+        # anything that can re-seat parameters (`_apply`: .cuda()/.to()/.float(); load_state_dict)
+        if self._param_cache is None:
+            self._param_cache = list(self.state_dict(keep_vars=True).items())
+        return tuple((v.data_ptr(), v._version) for _, v in self._param_cache)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._param_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._param_cache = None
+        return super().load_state_dict(*args, **kwargs)
 
     @property
     def _engine(self):
@@ -244,8 +257,7 @@ class GitB200CaptioningModel(nn.Module):
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
             sl['engine'], sl['sig'] = h, None
             import os
-            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_lean', 'use_2cta', 'epi_direct', 'lanes', 'sm_reserve',
-                        'decode_ctas', 'prio_split', 'pdl_late', 'attn_pipe', 'kv_head_major'):
+            for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_2cta'):
                 v = os.environ.get('GITB200_' + opt.upper())      # debugging switches, e.g. GITB200_USE_2CTA=0
                 if v is not None:
                     _lib.check(lib.gitb200_set_option(h, opt.encode(), int(v)), h, 'set_option')
@@ -262,7 +274,12 @@ class GitB200CaptioningModel(nn.Module):
             return lib, stream
         if sig != sl['sig']:
             eng = sl['engine']
-            for key, p in self.state_dict(keep_vars=True).items():
+            for other in self._slots:         # the slots share this copy: nothing may be in flight while it is rewritten
+                if other['pending'] is not None:
+                    other['pending'].result()
+            if self._param_cache is None:
+                self._param_cache = list(self.state_dict(keep_vars=True).items())
+            for key, p in self._param_cache:
                 t = p.detach()
                 if t.dtype != torch.float32 or not t.is_contiguous():
                     t = t.float().contiguous()
@@ -286,7 +303,7 @@ class GitB200CaptioningModel(nn.Module):
             pass
 
     def set_engine_option(self, name, value):
-        """Engine switches: 'use_graph', 'use_pdl', 'use_chain' (0/1), 'lanes' (1..4 concurrent decode row groups)."""
+        """Engine switches (0/1): 'use_graph', 'use_pdl', 'use_chain', 'use_2cta'."""
         self._options[name] = int(value)
         for k in range(self.n_slots):
             if k == 0 or self._slots[k]['engine'] is not None:

@@ -143,17 +143,15 @@ int gitb200_generate_finish(gitb200_engine* h, int32_t* out_len_host);
 
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t gitb200_launch_count(const gitb200_engine* h);
-/* Engine switches (defaults in parentheses): use_graph (1) CUDA-graph replay of the decode step, use_pdl (1), use_chain (1)
- * flag-ordered decode chain, use_2cta (1), prio_split (0) decode loop on a high-priority stream, pdl_late (0, process-wide)
- * release the PDL successor only once the kernel's own dependency is met, sm_reserve / decode_ctas (0) SM partitioning
- * between batches in flight, lanes (1), use_lean (0), epi_direct (0). */
+/* Engine switches (defaults in parentheses): use_graph (1) CUDA-graph replay of the decode step, use_pdl (1) programmatic
+ * dependent launch inside the step, use_chain (1) flag-ordered decode chain, use_2cta (1) cta_group::2 encoder GEMMs. */
 int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value);
 
 /* ---- single-kernel entry points (unit tests, micro-benchmarks, ncu) -------------------------------- */
 /* C = A[M,K] * W[N,K]^T (+bias) (+act: 0 none, 1 QuickGELU, 2 erf-GELU) (+resid fp32 [M,N]).
  * a_dev, w_dev bf16; out fp32 or bf16.  transposed != 0 runs the swap-AB skinny path used by the decode
- * step (a_dev = activations [M<=256,K], w_dev = weight [N,K], out[M,N]); k_splits > 1 accumulates with
- * atomics into a zeroed fp32 out (transposed only). bn: tile width override (0 = heuristic). */
+ * step (a_dev = activations [M<=256,K], w_dev = weight [N,K], out[M,N]); k_splits > 1 (transposed only, raw
+ * fp32 out, no bias / act): every split stores its own partial sums, which are added in split order -- bit-reproducible. bn: tile width override (0 = heuristic). */
 int gitb200_op_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                     void* out_dev, int M, int N, int K, int act, int out_bf16, int transposed, int k_splits,
                     int bn, void* stream);
@@ -191,7 +189,7 @@ int gitb200_preproc_create(int device, gitb200_preproc** out);
 void gitb200_preproc_destroy(gitb200_preproc* p);
 const char* gitb200_preproc_last_error(const gitb200_preproc* p);
 int64_t gitb200_preproc_launch_count(const gitb200_preproc* p);
-/* Switches: "fast" (0/1) -- word-load kernels (same results) where their alignment preconditions hold. */
+/* Reserved for future switches (none at present: every call returns non-zero). */
 int gitb200_preproc_set_option(gitb200_preproc* p, const char* name, int64_t value);
 /* src: packed uint8 RGB images, on the device (src_on_host == 0) or in host memory (pinned or pageable; copied to the
  * device on `stream` first).  mean3 / std3: host float[3].  Work is enqueued on `stream`; a second call on the same

@@ -33,3 +33,14 @@ def greedy_margins(raw_logits, tokens_in, eos=102):
         z.scatter_(1, tokens_in[:, None], -10000.0)
     top = z.topk(2, dim=1).values
     return top[:, 0] - top[:, 1]
+
+
+def golden_greedy_margins(g, i, tokens_in):
+    """The same margin from what a golden file stores (the reference's top-4 raw logits per row and step): the no-repeat
+    scatter removes the input token from the ranking (never on the first step)."""
+    vals, idx = g['step_top4_val'][i], g['step_top4_idx'][i]
+    out = np.zeros(vals.shape[0], dtype=np.float64)
+    for r in range(vals.shape[0]):
+        keep = [v for v, t in zip(vals[r], idx[r]) if tokens_in is None or t != int(tokens_in[r])]
+        out[r] = keep[0] - keep[1]
+    return out

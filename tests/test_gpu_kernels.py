@@ -95,8 +95,8 @@ def test_gemm_epilogues(act, out_bf16, use_resid):
 
 
 @pytest.mark.parametrize('rows,feats,K,splits', [
-    (64, 2304, 768, 1), (64, 768, 768, 2), (64, 768, 3072, 4), (5, 768, 768, 1), (1, 3072, 768, 1),
-    (128, 768, 3072, 4), (64, 30522, 768, 1), (200, 1024, 768, 1),
+    (64, 2304, 768, 1), (64, 2304, 768, 3), (64, 768, 768, 6), (64, 768, 3072, 8), (5, 768, 768, 1), (1, 3072, 768, 1),
+    (128, 768, 3072, 4), (256, 768, 3072, 8), (64, 30522, 768, 1), (200, 1024, 768, 1),
 ])
 def test_gemm_skinny_transposed(rows, feats, K, splits):
     x, w = _rand((rows, K), 1.0, 7), _rand((feats, K), 0.05, 8)
@@ -104,20 +104,8 @@ def test_gemm_skinny_transposed(rows, feats, K, splits):
     out = _gemm(x, w, bias, None, 0, False, True, splits)
     ref = _ref_gemm(x, w, bias)
     assert (out - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
-
-
-@pytest.mark.parametrize('rows,feats,K,splits,act,bf16', [
-    (64, 2304, 768, 1, 0, False), (64, 768, 768, 1, 0, False), (64, 3072, 768, 1, 2, True), (64, 768, 3072, 4, 0, False),
-    (5, 768, 768, 1, 0, False), (1, 3072, 768, 1, 2, True), (33, 768, 3072, 4, 0, False),
-])
-def test_gemm_skinny_lean_mma(rows, feats, K, splits, act, bf16):
-    """Decode-step GEMM path of skinny.cuh (mma.sync, weights prefetched, intra-CTA k-split reduction)."""
-    x, w = _rand((rows, K), 1.0, 13), _rand((feats, K), 0.05, 14)
-    bias = _rand((feats,), 0.5, 15, torch.float32) if splits == 1 else None
-    out = _gemm(x, w, bias, None, act, bf16, 2, splits)
-    ref = _ref_gemm(x, w, bias, None, act)
-    tol = 3e-2 if bf16 else 2e-3
-    assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    if splits > 1:     # split-K partial buffers are summed in split order: bit-identical from run to run
+        assert torch.equal(out, _gemm(x, w, bias, None, 0, False, True, splits))
 
 
 def test_gemm_skinny_gelu_bf16():
