@@ -535,4 +535,182 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   chain_signal(p.chain);
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32-grade parity mode (engine option "parity"): attention in plain fp32 -- q, k, v and both K/V caches stay fp32 and the
+// context rows leave in the GEMMs' split operand format [hi | lo | hi].  One warp per (sequence, head, query row); scores
+// live in shared memory.  Not a fast path: it exists so that the whole engine can be compared with the fp32 reference at
+// the 1e-3 logit tolerance of BASELINE.json's north star.
+// ------------------------------------------------------------------------------------------------
+struct AttnF32Params {
+  const float* q;
+  const float* k;
+  const float* v;
+  __nv_bfloat16* out;            // split3 rows: [S, 3 * d_model] per batch element
+  int B, S, H, d_model;
+  long long q_rs, kv_rs, q_bs, kv_bs, o_bs;   // row / batch strides in elements (output row stride = 3 * d_model)
+};
+
+__device__ __forceinline__ void store_split3_pair(__nv_bfloat16* row, int d_model, int col, float a, float b) {
+  uint32_t hi, lo;
+  pack_split2(a, b, hi, lo);
+  *reinterpret_cast<uint32_t*>(row + col) = hi;
+  *reinterpret_cast<uint32_t*>(row + d_model + col) = lo;
+  *reinterpret_cast<uint32_t*>(row + 2 * d_model + col) = hi;
+}
+
+__global__ void __launch_bounds__(128) attn_f32_kernel(const AttnF32Params p) {
+  extern __shared__ float attn_f32_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q_s = attn_f32_smem + warp * (64 + p.S);
+  float* sc = q_s + 64;
+  const long long item = static_cast<long long>(blockIdx.x) * 4 + warp;
+  const long long total = static_cast<long long>(p.B) * p.H * p.S;
+  if (item >= total) return;
+  const int row = static_cast<int>(item % p.S);
+  const int h = static_cast<int>((item / p.S) % p.H);
+  const int b = static_cast<int>(item / (static_cast<long long>(p.S) * p.H));
+  const float* qg = p.q + b * p.q_bs + static_cast<long long>(row) * p.q_rs + h * 64;
+  const float* kg = p.k + b * p.kv_bs + h * 64;
+  const float* vg = p.v + b * p.kv_bs + h * 64;
+  q_s[lane] = qg[lane] * 0.125f;             // Q / sqrt(64) before the product (reference layers/bert/modeling_bert.py:42-43)
+  q_s[lane + 32] = qg[lane + 32] * 0.125f;
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j0 = 0; j0 < p.S; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < p.S) {
+      const float4* kr = reinterpret_cast<const float4*>(kg + static_cast<long long>(j) * p.kv_rs);
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float4 kk = kr[d];
+        a = fmaf(q_s[4 * d], kk.x, a); a = fmaf(q_s[4 * d + 1], kk.y, a);
+        a = fmaf(q_s[4 * d + 2], kk.z, a); a = fmaf(q_s[4 * d + 3], kk.w, a);
+      }
+      sc[j] = a;
+      mx = fmaxf(mx, a);
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < p.S; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < p.S; ++j) {
+    const float2 vv = *reinterpret_cast<const float2*>(vg + static_cast<long long>(j) * p.kv_rs + 2 * lane);
+    a0 = fmaf(sc[j], vv.x, a0);
+    a1 = fmaf(sc[j], vv.y, a1);
+  }
+  __nv_bfloat16* orow = p.out + b * p.o_bs + static_cast<long long>(row) * 3 * p.d_model;
+  store_split3_pair(orow, p.d_model, h * 64 + 2 * lane, a0 / sum, a1 / sum);
+}
+
+struct DecAttnF32Params {
+  const float* qkv;               // split-K partial sums of this step's q | k | v, as in DecAttnParams
+  int n_partials;
+  long long partial_stride;
+  const float* bqkv;
+  const float* img_k;             // fp32 [B, M, D]
+  const float* img_v;
+  float* txt_k;                   // fp32 [R, T_alloc, D]
+  float* txt_v;
+  const int* src_row;
+  __nv_bfloat16* ctx;             // split3 rows [R, 3 * D]
+  int R, beam, M, T_alloc, D;
+  const StepState* state;
+  int pos_fixed;
+  ChainSync chain;
+};
+
+// one warp per (sequence r, head h); 4 warps per CTA
+__global__ void __launch_bounds__(128) decode_attn_f32_kernel(const DecAttnF32Params p) {
+  extern __shared__ float attn_f32_smem[];
+  griddep_launch_early();
+  bool finished;
+  if (p.chain.counters != nullptr) {
+    finished = (p.state != nullptr && p.state->finished);
+    if (!finished) chain_wait(p.chain);
+  } else {
+    griddep_wait();
+    finished = (p.state != nullptr && p.state->finished);
+  }
+  if (finished) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = p.D, H = D / 64;
+  const int pos = (p.state != nullptr) ? p.state->pos : p.pos_fixed;
+  const int n_keys = p.M + pos + 1;
+  float* q_s = attn_f32_smem + warp * (192 + p.M + p.T_alloc);
+  float* k_s = q_s + 64;
+  float* v_s = q_s + 128;
+  float* sc = q_s + 192;
+  const int item = blockIdx.x * 4 + warp;
+  if (item < p.R * H) {
+    const int r = item / H, h = item - r * H;
+    const int b = r / p.beam;
+    const float* row = p.qkv + static_cast<long long>(r) * 3 * D + h * 64;
+    const float* bias = p.bqkv + h * 64;
+    for (int d = lane; d < 64; d += 32) {
+      q_s[d] = (ld_partials(row + d, p.n_partials, p.partial_stride) + bias[d]) * 0.125f;
+      const float kn = ld_partials(row + D + d, p.n_partials, p.partial_stride) + bias[D + d];
+      const float vn = ld_partials(row + 2 * D + d, p.n_partials, p.partial_stride) + bias[2 * D + d];
+      k_s[d] = kn;
+      v_s[d] = vn;
+      p.txt_k[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = kn;
+      p.txt_v[(static_cast<long long>(r) * p.T_alloc + pos) * D + h * 64 + d] = vn;
+    }
+    __syncwarp();
+    auto key_ptr = [&](int j, bool want_v) -> const float* {   // row of key j (j != newest)
+      if (j < p.M) return (want_v ? p.img_v : p.img_k) + (static_cast<long long>(b) * p.M + j) * D + h * 64;
+      const int t = j - p.M;
+      const int pr = (p.src_row != nullptr) ? p.src_row[r * p.T_alloc + t] : r;
+      return (want_v ? p.txt_v : p.txt_k) + (static_cast<long long>(pr) * p.T_alloc + t) * D + h * 64;
+    };
+    float mx = -INFINITY;
+    for (int j0 = 0; j0 < n_keys; j0 += 32) {
+      const int j = j0 + lane;
+      if (j < n_keys) {
+        float a = 0.f;
+        if (j == n_keys - 1) {
+#pragma unroll
+          for (int d = 0; d < 64; ++d) a = fmaf(q_s[d], k_s[d], a);
+        } else {
+          const float4* kr = reinterpret_cast<const float4*>(key_ptr(j, false));
+#pragma unroll
+          for (int d = 0; d < 16; ++d) {
+            const float4 kk = kr[d];
+            a = fmaf(q_s[4 * d], kk.x, a); a = fmaf(q_s[4 * d + 1], kk.y, a);
+            a = fmaf(q_s[4 * d + 2], kk.z, a); a = fmaf(q_s[4 * d + 3], kk.w, a);
+          }
+        }
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n_keys; j += 32) {
+      const float e = expf(sc[j] - mx);
+      sc[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j + 1 < n_keys; ++j) {
+      const float2 vv = *reinterpret_cast<const float2*>(key_ptr(j, true) + 2 * lane);
+      a0 = fmaf(sc[j], vv.x, a0);
+      a1 = fmaf(sc[j], vv.y, a1);
+    }
+    a0 = fmaf(sc[n_keys - 1], v_s[2 * lane], a0);
+    a1 = fmaf(sc[n_keys - 1], v_s[2 * lane + 1], a1);
+    store_split3_pair(p.ctx + static_cast<long long>(r) * 3 * D, D, h * 64 + 2 * lane, a0 / sum, a1 / sum);
+  }
+  chain_signal(p.chain);
+}
+
 }  // namespace gitb200

@@ -1,0 +1,730 @@
+// One persistent kernel per greedy decode step (<= 64 sequences): the 6 decoder layers, the tied LM head with the
+// arg-max / log-sum-exp folded into it, the reference's greedy bookkeeping and the next step's token embedding
+// (reference layers/decoder.py:313-417, 65-78; layers/bert/modeling_bert.py:92-334) -- replacing the 45-launch chain of
+// gitb200.cu::step_layers for that case.
+//
+// Why: at <= 64 rows every kernel of the chain is latency bound (TMA -> tcgen05 -> TMEM -> epilogue -> flag, ~7 us per
+// hop, 341 us per step against an HBM floor of 59 us).  Here the HBM stream is decoupled from the dependency chain:
+//   * 148 CTAs (one per SM, cooperative launch), 8 compute warps + 1 producer warp each;
+//   * every byte the step reads from HBM that does NOT depend on the step -- the weight slice a CTA owns in each GEMM
+//     phase and the image K/V slices of its attention items -- flows through a 12 x 16 KB shared-memory ring that the
+//     producer warp fills in program order with TMA (bulk copies of pre-packed weight tiles, 128-row swizzled boxes of
+//     the K/V cache), running as far ahead of the compute warps as the ring allows, across phase boundaries;
+//   * phases (QKV | attention | out-proj | LN | fc1 | fc2 | LN per layer, then LM head | selection + embedding) are
+//     separated by a grid barrier (one release-add + acquire-spin on a global counter); what crosses a barrier is only
+//     the <= 64-row activations, read straight from L2 into mma.sync fragments;
+//   * weights are stationary per CTA: a GEMM phase gives CTA c the output features [f0, f0 + n) over the FULL reduction
+//     (no split-K, no partial buffers, bit-reproducible); the 8 warps split it 4 row tiles x 2 K halves.
+// The skinny GEMMs and the 1-row attention are HBM-bound byte work (arithmetic intensity ~rows FLOP/B): they use the
+// warp-level mma.sync path fed from shared memory; tcgen05 / TMEM stay with the compute-bound encoder and prefill GEMMs.
+#pragma once
+#include "ptx.cuh"
+#include "rowops.cuh"
+
+namespace gitb200 {
+
+constexpr int kMegaComputeWarps = 8;
+constexpr int kMegaThreads = (kMegaComputeWarps + 1) * 32;
+constexpr int kMegaSlots = 12;
+constexpr int kMegaSlotBytes = 16384;
+constexpr int kMegaTileBytes = 12288;      // 8 output features x 768 k x bf16, in mma-fragment order (pack_tiles_kernel)
+constexpr int kMegaKvRows = 128;           // K/V rows per ring slot (128 B per row and head)
+constexpr int kMegaMaxRows = 64;
+constexpr int kMegaD = 768, kMegaF = 3072, kMegaH = 12;
+constexpr unsigned int kMegaSpinLimit = 1u << 27;
+
+struct MegaLayer {
+  const uint8_t* wqkv;     // [288] tiles: features 8t .. 8t+7 of the fused q | k | v projection
+  const uint8_t* wo;       // [96]
+  const uint8_t* w1;       // [384]
+  const uint8_t* w2;       // [96][4]: feature tile x 768-wide k slice
+  const float* bqkv; const float* bo; const float* b1; const float* b2;
+  const float* lnag; const float* lnab; const float* lnog; const float* lnob;
+  __nv_bfloat16* txt_k;    // [R, T_alloc, 768]
+  __nv_bfloat16* txt_v;
+};
+
+struct MegaParams {
+  MegaLayer layer[6];
+  const uint8_t* lm;       // [ceil(V / 8)] tiles of the tied word-embedding matrix
+  const float* lm_bias;
+  const float* words;      // fp32 [V, 768] (embedding gather)
+  const float* positions;  // fp32 [max_pos, 768]
+  const float* lnemb_g; const float* lnemb_b;
+  int R, M, T_alloc, V, n_layers;
+  // activations (global, L2 resident)
+  float* x;                // [R, 768] residual stream (post-LayerNorm)
+  float* y;                // [R, 768] pre-LayerNorm sum
+  __nv_bfloat16* hb;       // [R, 768] bf16 copy of x (GEMM operand)
+  __nv_bfloat16* qb;       // [R, 768] q (+bias) / 8
+  __nv_bfloat16* ctx;      // [R, 768]
+  __nv_bfloat16* ub;       // [R, 3072]
+  float* part_max; float* part_sum; int* part_arg;   // [R, gridDim.x] LM-head partials
+  // search state (the same objects greedy_select_kernel works on)
+  StepState* state;
+  long long* tokens_out; int max_steps; float* logprob_sum; long long* next_token; const long long* forced;
+  float* step_logits; int eos;
+  unsigned int* barrier;   // [2] grid-barrier counters, used alternately by successive steps
+  int* error;              // set non-zero when a bounded spin gave up (the host reports it)
+};
+
+// ---- packing: [N, K] row-major bf16 -> tiles of 8 features x 768 k in fragment order ------------------------------------
+// Tile layout: 48 k-steps x 32 lanes x 8 bytes.  Lane (g = lane / 4, t = lane % 4) of k-step s holds the four k values
+// k0 + 32 * (s / 2) + 8 t + 4 (s % 2) + {0, 1, 2, 3} of feature 8 tile + g: the B fragment (b0 = first pair, b1 = second
+// pair) of an m16n8k16 MMA whose k index has been permuted so that the matching A fragment is 8 CONTIGUOUS bf16 per
+// thread and k-step pair (one 128-bit load from the row-major activation matrix).
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const __nv_bfloat16* __restrict__ W, long long ldw, int n_feat, int k0,
+                                                         uint8_t* __restrict__ dst, long long n_tiles, int tile_stride_tiles,
+                                                         int tile_offset) {
+  const long long total = n_tiles * 48 * 32;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int lane = static_cast<int>(i & 31);
+    const int s = static_cast<int>((i >> 5) % 48);
+    const long long tile = i / (48 * 32);
+    const int g = lane >> 2, t = lane & 3;
+    const long long f = tile * 8 + g;
+    const int k = k0 + 32 * (s >> 1) + 8 * t + 4 * (s & 1);
+    uint2 v = make_uint2(0u, 0u);
+    if (f < n_feat) v = *reinterpret_cast<const uint2*>(W + f * ldw + k);
+    *reinterpret_cast<uint2*>(dst + (tile * tile_stride_tiles + tile_offset) * kMegaTileBytes + (s * 32 + lane) * 8) = v;
+  }
+}
+
+// ---- small device helpers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (unsigned int i = 0; i < kMegaSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  return false;
+}
+
+struct MegaRing {
+  uint8_t* base;
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t idx;      // chunks consumed so far (identical in every compute warp)
+  int* error;
+  __device__ __forceinline__ const uint8_t* acquire() {
+    const uint32_t slot = idx % kMegaSlots;
+    if (!mbar_wait_bounded(&full[slot], (idx / kMegaSlots) & 1)) *error = 2;
+    return base + slot * kMegaSlotBytes;
+  }
+  __device__ __forceinline__ void release() {   // every compute warp, once per chunk
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[idx % kMegaSlots]);
+    ++idx;
+  }
+};
+
+// Grid barrier between phases (compute warps only: 256 threads; the producer warp never waits for a phase).
+__device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned int& epoch, int* error) {
+  named_bar_sync(1, kMegaComputeWarps * 32);
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+    unsigned int spins = 0;
+    while (ld_acquire_gpu(counter) < epoch) {
+      if (++spins > kMegaSpinLimit) { *error = 1; break; }
+    }
+  }
+  named_bar_sync(1, kMegaComputeWarps * 32);
+}
+
+// A operand of one GEMM phase: this warp's 16 rows x 384 k of a row-major bf16 activation matrix, straight from L2.
+struct MegaAFrag {
+  uint4 lo[12];   // row g     : 8 contiguous k per entry (two k-steps)
+  uint4 hi[12];   // row g + 8
+};
+__device__ __forceinline__ void mega_load_a(MegaAFrag& a, const __nv_bfloat16* A, long long lda, int rows, int mt, int kh, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = mt * 16 + g, r1 = r0 + 8;
+  const uint4* p0 = reinterpret_cast<const uint4*>(A + static_cast<long long>(r0) * lda + kh * 384 + 8 * t);
+  const uint4* p1 = reinterpret_cast<const uint4*>(A + static_cast<long long>(r1) * lda + kh * 384 + 8 * t);
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    a.lo[j] = (r0 < rows) ? __ldcg(p0 + 4 * j) : make_uint4(0, 0, 0, 0);
+    a.hi[j] = (r1 < rows) ? __ldcg(p1 + 4 * j) : make_uint4(0, 0, 0, 0);
+  }
+}
+// c += A(16 x 384 of this warp) * tile(8 features, this warp's k half)
+__device__ __forceinline__ void mega_mma_tile(float (&c)[4], const MegaAFrag& a, const uint8_t* tile, int kh, int lane) {
+  const uint2* bp = reinterpret_cast<const uint2*>(tile) + kh * 24 * 32 + lane;
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    const uint2 b0 = bp[(2 * j) * 32];
+    const uint2 b1 = bp[(2 * j + 1) * 32];
+    const uint32_t a0[4] = {a.lo[j].x, a.hi[j].x, a.lo[j].y, a.hi[j].y};
+    const uint32_t a1[4] = {a.lo[j].z, a.hi[j].z, a.lo[j].w, a.hi[j].w};
+    mma_bf16_16816(c, a0, b0.x, b0.y);
+    mma_bf16_16816(c, a1, b1.x, b1.y);
+  }
+}
+
+// Sum of the two K halves: the kh = 1 warp parks its accumulator in shared memory, its kh = 0 partner adds it.
+// Returns true in the warp that owns the result.  `red` = [2 buffers][4 row tiles][32 lanes][4] floats.
+__device__ __forceinline__ bool mega_combine(float (&c)[4], float* red, int buf, int mt, int kh, int lane) {
+  float4* slot = reinterpret_cast<float4*>(red) + (buf * 4 + mt) * 32 + lane;
+  if (kh == 1) *slot = make_float4(c[0], c[1], c[2], c[3]);
+  named_bar_sync(2 + mt, 64);
+  if (kh == 0) {
+    const float4 o = *slot;
+    c[0] += o.x; c[1] += o.y; c[2] += o.z; c[3] += o.w;
+  }
+  return kh == 0;
+}
+
+__device__ __forceinline__ float2 ldcg_f2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMegaThreads, 1)
+decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p) {
+  extern __shared__ __align__(1024) uint8_t mega_smem_raw[];
+  uint8_t* smem = mega_smem_raw + ((1024u - (smem_u32(mega_smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = smem;                                                  // 12 x 16 KB
+  float* red = reinterpret_cast<float*>(smem + kMegaSlots * kMegaSlotBytes);          // 2 x 4 x 32 x 4 floats = 4 KB
+  uint8_t* q_s = reinterpret_cast<uint8_t*>(red) + 4096;                 // 16 rows x 128 B (swizzled)
+  float* att_part = reinterpret_cast<float*>(q_s + 2048);                // [16 partials][68] floats
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(att_part) + 16 * 68 * 4);
+  uint64_t* empty = full + kMegaSlots;
+
+  StepState* st = p.state;
+  if (st->finished) return;                     // stable: only the previous launch's selection phase writes it
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const int R = p.R, M = p.M;
+  const int pos = st->pos, step = st->step, cur_len = st->cur_len;
+  const int n_kv = (M + kMegaKvRows - 1) / kMegaKvRows;
+  const int n_items = R * kMegaH;
+  const int my_cta_rev = G - 1 - cta;           // attention items are dealt from the last CTA down (those own fewer weights)
+  const int n_my_items = (n_items > my_cta_rev) ? (n_items - my_cta_rev + G - 1) / G : 0;
+  const int lm_tiles_total = (p.V + 7) / 8;
+  const int lm_per = (lm_tiles_total + G - 1) / G;
+  const int lm_t0 = cta * lm_per;
+  const int lm_n = max(0, min(lm_per, lm_tiles_total - lm_t0));
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmKV);
+    for (int s = 0; s < kMegaSlots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kMegaComputeWarps);
+    }
+    mbar_fence_init();
+    if (cta == 0) p.barrier[(step + 1) & 1] = 0;   // the counter the NEXT step will use
+  }
+  __syncthreads();
+
+  if (warp == kMegaComputeWarps) {
+    // ============================== producer: the step's HBM stream, in program order ==============================
+    if (lane == 0) {
+      uint32_t i = 0;
+      auto slot_ready = [&]() -> uint8_t* {
+        const uint32_t slot = i % kMegaSlots;
+        if (i >= kMegaSlots && !mbar_wait_bounded(&empty[slot], ((i / kMegaSlots) - 1) & 1)) *p.error = 3;
+        return ring + slot * kMegaSlotBytes;
+      };
+      auto tile = [&](const uint8_t* src) {
+        uint8_t* dst = slot_ready();
+        mbar_arrive_expect_tx(&full[i % kMegaSlots], kMegaTileBytes);
+        bulk_load_1d(dst, src, kMegaTileBytes, &full[i % kMegaSlots]);
+        ++i;
+      };
+      auto kv = [&](int row, int col) {
+        uint8_t* dst = slot_ready();
+        mbar_arrive_expect_tx(&full[i % kMegaSlots], kMegaSlotBytes);
+        tma_load_2d(dst, &tmKV, &full[i % kMegaSlots], col, row);
+        ++i;
+      };
+      for (int l = 0; l < p.n_layers; ++l) {
+        const MegaLayer& L = p.layer[l];
+        if (cta < 144) for (int j = 0; j < 2; ++j) tile(L.wqkv + static_cast<size_t>(cta * 2 + j) * kMegaTileBytes);
+        for (int k = 0; k < n_my_items; ++k) {
+          const int item = my_cta_rev + k * G;
+          const int b = item / kMegaH, h = item - b * kMegaH;
+          for (int c = 0; c < n_kv; ++c) {
+            kv((l * 2 + 0) * R * M + b * M + c * kMegaKvRows, h * 64);
+            kv((l * 2 + 1) * R * M + b * M + c * kMegaKvRows, h * 64);
+          }
+        }
+        if (cta < 96) tile(L.wo + static_cast<size_t>(cta) * kMegaTileBytes);
+        if (cta < 128) for (int j = 0; j < 3; ++j) tile(L.w1 + static_cast<size_t>(cta * 3 + j) * kMegaTileBytes);
+        if (cta < 96) for (int s = 0; s < 4; ++s) tile(L.w2 + static_cast<size_t>(cta * 4 + s) * kMegaTileBytes);
+      }
+      for (int j = 0; j < lm_n; ++j) tile(p.lm + static_cast<size_t>(lm_t0 + j) * kMegaTileBytes);
+    }
+    return;
+  }
+
+  // ================================== compute warps ==================================
+  MegaRing rg{ring, full, empty, 0u, p.error};
+  unsigned int* bar = p.barrier + (step & 1);
+  unsigned int epoch = 0;
+  const int mt = warp & 3, kh = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = mt * 16 + g, r1 = r0 + 8;
+  int red_buf = 0;
+
+  for (int l = 0; l < p.n_layers; ++l) {
+    const MegaLayer& L = p.layer[l];
+    // ------------------------------------------------ P1: q | k | v ------------------------------------------------
+    if (cta < 144) {
+      MegaAFrag a;
+      mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
+      for (int j = 0; j < 2; ++j) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint8_t* tb = rg.acquire();
+        mega_mma_tile(c, a, tb, kh, lane);
+        rg.release();
+        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+          const int f = (cta * 2 + j) * 8 + 2 * t;
+          const float2 bias = *reinterpret_cast<const float2*>(L.bqkv + f);
+          const int seg = f / kMegaD, fo = f - seg * kMegaD;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int r = hh ? r1 : r0;
+            if (r >= R) continue;
+            const float v0 = c[2 * hh] + bias.x, v1 = c[2 * hh + 1] + bias.y;
+            if (seg == 0) {
+              *reinterpret_cast<uint32_t*>(p.qb + static_cast<long long>(r) * kMegaD + fo) = pack_bf16(v0 * 0.125f, v1 * 0.125f);
+            } else {
+              __nv_bfloat16* dst = (seg == 1 ? L.txt_k : L.txt_v) + (static_cast<long long>(r) * p.T_alloc + pos) * kMegaD + fo;
+              *reinterpret_cast<uint32_t*>(dst) = pack_bf16(v0, v1);
+            }
+          }
+        }
+        red_buf ^= 1;
+      }
+    }
+    mega_grid_sync(bar, epoch, p.error);
+    // ------------------------------------------------ P2: attention ------------------------------------------------
+    for (int k = 0; k < n_my_items; ++k) {
+      const int item = my_cta_rev + k * G;
+      const int b = item / kMegaH, h = item - b * kMegaH;
+      // q tile: row 0 = this sequence's query (already scaled by 1/8), rows 1..15 zero; 128B-swizzled like the K/V boxes
+      if (tid < 128) {
+        const int row = tid >> 3, ch = tid & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row == 0) v = __ldcg(reinterpret_cast<const uint4*>(p.qb + static_cast<long long>(b) * kMegaD + h * 64) + ch);
+        *reinterpret_cast<uint4*>(q_s + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+      }
+      named_bar_sync(1, kMegaComputeWarps * 32);
+      uint32_t qa[4][4];
+      {
+        const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int chunk = 2 * kk + (lane >> 4);
+          ldmatrix_x4(qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], smem_u32(q_s) + row * 128 + ((chunk ^ (row & 7)) << 4));
+        }
+      }
+      float o[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f;       // row g of the q tile (only g == 0 is a real row)
+      constexpr float kLog2e = 1.44269504088896340736f;
+      for (int c = 0; c < n_kv; ++c) {
+        // ---- S = q K^T for this warp's 16 keys of the chunk ----
+        const uint32_t sK = smem_u32(rg.acquire());
+        float s[2][4];
+#pragma unroll
+        for (int jn = 0; jn < 2; ++jn) {
+          s[jn][0] = s[jn][1] = s[jn][2] = s[jn][3] = 0.f;
+          const int krow = 16 * warp + 8 * jn + (lane & 7);
+#pragma unroll
+          for (int kk2 = 0; kk2 < 2; ++kk2) {
+            const int chunk = 4 * kk2 + (lane >> 3);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(b0, b1, b2, b3, sK + krow * 128 + ((chunk ^ (krow & 7)) << 4));
+            mma_bf16_16816(s[jn], qa[2 * kk2], b0, b1);
+            mma_bf16_16816(s[jn], qa[2 * kk2 + 1], b2, b3);
+          }
+        }
+        rg.release();
+        const int key0 = c * kMegaKvRows + 16 * warp + 2 * t;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jn = 0; jn < 2; ++jn) {
+          if (key0 + 8 * jn >= M) s[jn][0] = -INFINITY;
+          if (key0 + 8 * jn + 1 >= M) s[jn][1] = -INFINITY;
+          mx = fmaxf(mx, fmaxf(s[jn][0], s[jn][1]));
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run, mx);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // all 16 keys of this warp masked so far
+        const float corr = exp2f((m_run - m_use) * kLog2e);         // m_run == -inf -> 0
+        m_run = m_new;
+        l_run *= corr;
+        uint32_t pa[4];
+#pragma unroll
+        for (int jn = 0; jn < 2; ++jn) {
+          const float p0 = exp2f((s[jn][0] - m_use) * kLog2e);
+          const float p1 = exp2f((s[jn][1] - m_use) * kLog2e);
+          l_run += p0 + p1;
+          pa[2 * jn] = pack_bf16(p0, p1);
+          pa[2 * jn + 1] = 0u;                                      // rows 8..15 of the q tile do not exist
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
+        // ---- O += P V ----
+        const uint32_t sV = smem_u32(rg.acquire());
+        {
+          const int vrow = 16 * warp + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int chunk = 2 * jj + (lane >> 4);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(b0, b1, b2, b3, sV + vrow * 128 + ((chunk ^ (vrow & 7)) << 4));
+            mma_bf16_16816(o[2 * jj], pa, b0, b1);
+            mma_bf16_16816(o[2 * jj + 1], pa, b2, b3);
+          }
+        }
+        rg.release();
+      }
+      l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+      l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+      // ---- text keys (this step's own K/V included): warp w takes positions w, w + 8, ...; lane = 2 head dims ----
+      float tm = -INFINITY, tl = 0.f, to0 = 0.f, to1 = 0.f;
+      {
+        const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(q_s + ((lane >> 2) << 4) + ((lane & 3) << 2));  // row 0: chunk ^ 0
+        const float qx = __bfloat162float(q2.x), qy = __bfloat162float(q2.y);
+        for (int j = warp; j <= pos; j += kMegaComputeWarps) {
+          const long long off = (static_cast<long long>(b) * p.T_alloc + j) * kMegaD + h * 64 + 2 * lane;
+          const uint32_t kr = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_k + off));
+          const uint32_t vr = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_v + off));
+          const float sc = warp_sum(qx * bf16_lo(kr) + qy * bf16_hi(kr));
+          const float mn = fmaxf(tm, sc);
+          const float cr = exp2f((tm - mn) * kLog2e);
+          const float pe = exp2f((sc - mn) * kLog2e);
+          tl = tl * cr + pe;
+          to0 = to0 * cr + pe * bf16_lo(vr);
+          to1 = to1 * cr + pe * bf16_hi(vr);
+          tm = mn;
+        }
+      }
+      // ---- merge the 16 partial softmax states (8 image-key partials, 8 text-key partials) ----
+      if (g == 0) {
+        float* pp = att_part + warp * 68;
+        if (t == 0) { pp[64] = m_run; pp[65] = l_run; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { pp[8 * j + 2 * t] = o[j][0]; pp[8 * j + 2 * t + 1] = o[j][1]; }
+      }
+      {
+        float* pp = att_part + (8 + warp) * 68;
+        if (lane == 0) { pp[64] = tm; pp[65] = tl; }
+        pp[2 * lane] = to0;
+        pp[2 * lane + 1] = to1;
+      }
+      named_bar_sync(1, kMegaComputeWarps * 32);
+      if (tid < 64) {
+        float mm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mm = fmaxf(mm, att_part[i * 68 + 64]);
+        float lsum = 0.f, acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float mi = att_part[i * 68 + 64];
+          const float w = (mi == -INFINITY) ? 0.f : exp2f((mi - mm) * kLog2e);
+          lsum += att_part[i * 68 + 65] * w;
+          acc += att_part[i * 68 + tid] * w;
+        }
+        p.ctx[static_cast<long long>(b) * kMegaD + h * 64 + tid] = __float2bfloat16_rn(acc / lsum);
+      }
+      named_bar_sync(1, kMegaComputeWarps * 32);      // q_s / att_part are rewritten by the next item
+    }
+    mega_grid_sync(bar, epoch, p.error);
+    // ------------------------------------------------ P3: attention output projection (+bias +residual) ------------------
+    if (cta < 96) {
+      MegaAFrag a;
+      mega_load_a(a, p.ctx, kMegaD, R, mt, kh, lane);
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint8_t* tb = rg.acquire();
+      mega_mma_tile(c, a, tb, kh, lane);
+      rg.release();
+      if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+        const int f = cta * 8 + 2 * t;
+        const float2 bias = *reinterpret_cast<const float2*>(L.bo + f);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int r = hh ? r1 : r0;
+          if (r >= R) continue;
+          const float2 xr = ldcg_f2(p.x + static_cast<long long>(r) * kMegaD + f);
+          *reinterpret_cast<float2*>(p.y + static_cast<long long>(r) * kMegaD + f) =
+              make_float2(xr.x + (c[2 * hh] + bias.x), xr.y + (c[2 * hh + 1] + bias.y));
+        }
+      }
+      red_buf ^= 1;
+    }
+    mega_grid_sync(bar, epoch, p.error);
+    // ------------------------------------------------ P4 / P7: LayerNorm(y) -> x, hb (one warp per row) -------------------
+    auto layer_norm_rows = [&](const float* gamma, const float* beta) {
+      const int row = cta * kMegaComputeWarps + warp;
+      if (row < R) {
+        float4 v[6];
+        const float4* yp = reinterpret_cast<const float4*>(p.y + static_cast<long long>(row) * kMegaD);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = __ldcg(yp + i * 32 + lane);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float mean = warp_sum(s) * (1.0f / kMegaD);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
+          ss += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.0f / kMegaD) + 1e-12f);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+          const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+          float4 ov;
+          ov.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+          ov.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+          ov.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+          ov.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+          reinterpret_cast<float4*>(p.x + static_cast<long long>(row) * kMegaD)[i * 32 + lane] = ov;
+          uint2 pk;
+          pk.x = pack_bf16(ov.x, ov.y);
+          pk.y = pack_bf16(ov.z, ov.w);
+          reinterpret_cast<uint2*>(p.hb + static_cast<long long>(row) * kMegaD)[i * 32 + lane] = pk;
+        }
+      }
+    };
+    layer_norm_rows(L.lnag, L.lnab);
+    mega_grid_sync(bar, epoch, p.error);
+    // ------------------------------------------------ P5: fc1 + erf-GELU ------------------------------------------------
+    if (cta < 128) {
+      MegaAFrag a;
+      mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
+      for (int j = 0; j < 3; ++j) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint8_t* tb = rg.acquire();
+        mega_mma_tile(c, a, tb, kh, lane);
+        rg.release();
+        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+          const int f = (cta * 3 + j) * 8 + 2 * t;
+          const float2 bias = *reinterpret_cast<const float2*>(L.b1 + f);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int r = hh ? r1 : r0;
+            if (r >= R) continue;
+            *reinterpret_cast<uint32_t*>(p.ub + static_cast<long long>(r) * kMegaF + f) =
+                pack_bf16(apply_act(c[2 * hh] + bias.x, ACT_GELU_ERF), apply_act(c[2 * hh + 1] + bias.y, ACT_GELU_ERF));
+          }
+        }
+        red_buf ^= 1;
+      }
+    }
+    mega_grid_sync(bar, epoch, p.error);
+    // ------------------------------------------------ P6: fc2 (+bias +residual), full K = 3072 in four slices ------------
+    if (cta < 96) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int sl = 0; sl < 4; ++sl) {
+        MegaAFrag a;
+        mega_load_a(a, p.ub + sl * kMegaD, kMegaF, R, mt, kh, lane);
+        const uint8_t* tb = rg.acquire();
+        mega_mma_tile(c, a, tb, kh, lane);
+        rg.release();
+      }
+      if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+        const int f = cta * 8 + 2 * t;
+        const float2 bias = *reinterpret_cast<const float2*>(L.b2 + f);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int r = hh ? r1 : r0;
+          if (r >= R) continue;
+          const float2 xr = ldcg_f2(p.x + static_cast<long long>(r) * kMegaD + f);
+          *reinterpret_cast<float2*>(p.y + static_cast<long long>(r) * kMegaD + f) =
+              make_float2(xr.x + (c[2 * hh] + bias.x), xr.y + (c[2 * hh + 1] + bias.y));
+        }
+      }
+      red_buf ^= 1;
+    }
+    mega_grid_sync(bar, epoch, p.error);
+    layer_norm_rows(L.lnog, L.lnob);
+    mega_grid_sync(bar, epoch, p.error);
+  }
+
+  // ------------------------------------------------ LM head with the greedy statistics folded in ---------------------------
+  // Each kh = 0 warp keeps, for its 2 x 2 (row, column-parity) positions, the running (max, arg max, sum exp) over this
+  // CTA's features -- the logits themselves never leave the SM (unless the parity hook asks for them).
+  {
+    const bool first = (step == 0);
+    long long last0 = -1, last1 = -1;
+    if (r0 < R) last0 = p.next_token[r0];
+    if (r1 < R) last1 = p.next_token[r1];
+    float smax[2] = {-INFINITY, -INFINITY}, ssum[2] = {0.f, 0.f};
+    int sarg[2] = {0x7fffffff, 0x7fffffff};
+    if (lm_n > 0) {
+      MegaAFrag a;
+      mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
+      for (int j = 0; j < lm_n; ++j) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint8_t* tb = rg.acquire();
+        mega_mma_tile(c, a, tb, kh, lane);
+        rg.release();
+        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+          const int f = (lm_t0 + j) * 8 + 2 * t;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int r = hh ? r1 : r0;
+            if (r >= R) continue;
+            const long long last = hh ? last1 : last0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = f + e;
+              if (col >= p.V) continue;
+              float v = c[2 * hh + e] + __ldg(p.lm_bias + col);
+              if (p.step_logits != nullptr) p.step_logits[(static_cast<long long>(step) * R + r) * p.V + col] = v;
+              if (!first && col == static_cast<int>(last)) v = -10000.0f;        // no-repeat (reference :330)
+              if (v > smax[hh]) {            // columns arrive in increasing order: the lowest index wins exact ties
+                ssum[hh] = ssum[hh] * __expf(smax[hh] - v) + 1.0f;
+                smax[hh] = v;
+                sarg[hh] = col;
+              } else {
+                ssum[hh] += __expf(v - smax[hh]);
+              }
+            }
+          }
+        }
+        red_buf ^= 1;
+      }
+    }
+    if (kh == 0) {
+      // combine the 4 lanes of a quad (they hold the same rows, interleaved column pairs)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int o2 = 1; o2 <= 2; o2 <<= 1) {
+          const float m_o = __shfl_xor_sync(0xffffffffu, smax[hh], o2);
+          const float s_o = __shfl_xor_sync(0xffffffffu, ssum[hh], o2);
+          const int a_o = __shfl_xor_sync(0xffffffffu, sarg[hh], o2);
+          const float mn = fmaxf(smax[hh], m_o);
+          const float sa = (smax[hh] == -INFINITY) ? 0.f : __expf(smax[hh] - mn);
+          const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - mn);
+          ssum[hh] = ssum[hh] * sa + s_o * sb;
+          if (m_o > smax[hh] || (m_o == smax[hh] && a_o < sarg[hh])) sarg[hh] = a_o;
+          smax[hh] = mn;
+        }
+        const int r = hh ? r1 : r0;
+        if (t == 0 && r < R) {
+          p.part_max[static_cast<long long>(r) * G + cta] = smax[hh];
+          p.part_sum[static_cast<long long>(r) * G + cta] = ssum[hh];
+          p.part_arg[static_cast<long long>(r) * G + cta] = sarg[hh];
+        }
+      }
+    }
+  }
+  mega_grid_sync(bar, epoch, p.error);
+
+  // ------------------------------------------------ selection (greedy bookkeeping) + next token's embedding ----------------
+  if (cta < R && warp == 0) {
+    const int row = cta;
+    const bool first = (step == 0);
+    float gm = -INFINITY, gs = 0.f;
+    int ga = 0x7fffffff;
+    for (int k = lane; k < G; k += 32) {           // increasing CTA order = increasing column order
+      const float pm = __ldcg(p.part_max + static_cast<long long>(row) * G + k);
+      const float ps = __ldcg(p.part_sum + static_cast<long long>(row) * G + k);
+      const int pa2 = __ldcg(p.part_arg + static_cast<long long>(row) * G + k);
+      const float mn = fmaxf(gm, pm);
+      const float sa = (gm == -INFINITY) ? 0.f : __expf(gm - mn);
+      const float sb = (pm == -INFINITY) ? 0.f : __expf(pm - mn);
+      gs = gs * sa + ps * sb;
+      if (pm > gm || (pm == gm && pa2 < ga)) ga = pa2;
+      gm = mn;
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+      const float m_o = __shfl_xor_sync(0xffffffffu, gm, o2);
+      const float s_o = __shfl_xor_sync(0xffffffffu, gs, o2);
+      const int a_o = __shfl_xor_sync(0xffffffffu, ga, o2);
+      const float mn = fmaxf(gm, m_o);
+      const float sa = (gm == -INFINITY) ? 0.f : __expf(gm - mn);
+      const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - mn);
+      gs = gs * sa + s_o * sb;
+      if (m_o > gm || (m_o == gm && a_o < ga)) ga = a_o;
+      gm = mn;
+    }
+    const long long last = p.next_token[row];
+    const bool row_done = (!first) && (last == p.eos);
+    long long tok = row_done ? p.eos : ga;                         // EOS forcing: one-hot distribution, log-prob 0
+    const float lp = row_done ? 0.f : -logf(gs);
+    long long nxt = tok;
+    if (p.forced != nullptr) nxt = p.forced[static_cast<long long>(row) * p.max_steps + cur_len];
+    if (lane == 0) {
+      p.tokens_out[static_cast<long long>(row) * p.max_steps + cur_len] = tok;
+      p.logprob_sum[row] += lp;
+      p.next_token[row] = nxt;
+    }
+    // embedding of the token the next step feeds: e = LN(words[nxt] + positions[pos + 1], eps 1e-8)
+    {
+      long long tk = nxt < 0 ? 0 : (nxt >= p.V ? p.V - 1 : nxt);
+      const float4* wp = reinterpret_cast<const float4*>(p.words + tk * kMegaD);
+      const float4* pp = reinterpret_cast<const float4*>(p.positions + static_cast<long long>(pos + 1) * kMegaD);
+      float4 v[6];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float4 a = __ldg(wp + i * 32 + lane);
+        const float4 b2 = __ldg(pp + i * 32 + lane);
+        v[i] = make_float4(a.x + b2.x, a.y + b2.y, a.z + b2.z, a.w + b2.w);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      const float mean = warp_sum(s) * (1.0f / kMegaD);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
+        ss += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+      }
+      const float rstd = rsqrtf(warp_sum(ss) * (1.0f / kMegaD) + 1e-8f);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float4 gmm = __ldg(reinterpret_cast<const float4*>(p.lnemb_g) + i * 32 + lane);
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(p.lnemb_b) + i * 32 + lane);
+        float4 ov = make_float4((v[i].x - mean) * rstd * gmm.x + bt.x, (v[i].y - mean) * rstd * gmm.y + bt.y,
+                                (v[i].z - mean) * rstd * gmm.z + bt.z, (v[i].w - mean) * rstd * gmm.w + bt.w);
+        reinterpret_cast<float4*>(p.x + static_cast<long long>(row) * kMegaD)[i * 32 + lane] = ov;
+        uint2 pk;
+        pk.x = pack_bf16(ov.x, ov.y);
+        pk.y = pack_bf16(ov.z, ov.w);
+        reinterpret_cast<uint2*>(p.hb + static_cast<long long>(row) * kMegaD)[i * 32 + lane] = pk;
+      }
+    }
+    if (lane == 0) {
+      // loop state: the row that draws the last ticket advances it (same protocol as greedy_select_kernel)
+      if (nxt != p.eos) atomicAdd(&st->not_eos, 1);
+      __threadfence();
+      const unsigned int tr = atomicAdd(&st->ticket, 1u);
+      if (tr == static_cast<unsigned int>(R) - 1) {
+        __threadfence();
+        const int not_eos = atomicAdd(&st->not_eos, 0);
+        st->ticket = 0;
+        st->not_eos = 0;
+        st->cur_len = cur_len + 1;
+        st->final_len = cur_len + 1;
+        st->pos = pos + 1;
+        st->step = step + 1;
+        if (not_eos == 0) {
+          st->finished = 1;
+          if (first) st->empty_caption = 1;
+        }
+        if (cur_len + 1 >= p.max_steps) st->finished = 1;
+        __threadfence();
+      }
+    }
+  }
+}
+
+constexpr size_t kMegaSmemBytes = 1024 + kMegaSlots * kMegaSlotBytes + 4096 + 2048 + 16 * 68 * 4 + 2 * kMegaSlots * 8 + 64;
+
+}  // namespace gitb200

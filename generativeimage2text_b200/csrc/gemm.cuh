@@ -40,13 +40,14 @@ struct GemmParams {
   int row_offset;
   const int* skip;            // device flag: non-zero -> the whole launch is a no-op (finished decode)
   unsigned long long* dbg;    // optional [8] %globaltimer stamps of CTA 0 (profiling aid; null in production)
+  int split3;                 // bf16 output in the parity mode's operand format: row = [hi | lo | hi] (3 x N columns, ldo = 3N)
   int pdl;                    // launched with programmatic dependent launch: prefetch weights, then griddep_wait()
   ChainSync chain;            // flag-based ordering inside the decode step (see ptx.cuh); counters == null: off
 };
 
 // Epilogue variants are compile-time (the runtime-flag version spent ~700 warp instructions per 32x32 chunk,
 // which made every K=768 GEMM of the encoder epilogue-issue bound).
-constexpr int EPI_TRANSPOSED = 1, EPI_BF16 = 2, EPI_RESID = 4, EPI_PARTIAL = 8, EPI_ACT_SHIFT = 4;
+constexpr int EPI_TRANSPOSED = 1, EPI_BF16 = 2, EPI_RESID = 4, EPI_PARTIAL = 8, EPI_ACT_SHIFT = 4, EPI_SPLIT3 = 64;
 constexpr int epi_code(bool transposed, bool bf16, bool resid, bool partial, int act) {
   return (transposed ? EPI_TRANSPOSED : 0) | (bf16 ? EPI_BF16 : 0) | (resid ? EPI_RESID : 0) | (partial ? EPI_PARTIAL : 0) |
          (act << EPI_ACT_SHIFT);
@@ -104,6 +105,8 @@ __device__ __forceinline__ void epi_store_normal(const GemmParams& p, const uint
   constexpr bool kBf16 = (EPI & EPI_BF16) != 0;
   constexpr bool kResid = (EPI & EPI_RESID) != 0;
   constexpr int kAct = (EPI >> EPI_ACT_SHIFT) & 3;
+  constexpr bool kSplit3 = (EPI & EPI_SPLIT3) != 0;
+  static_assert(!kSplit3 || kBf16, "split3 is a bf16 output format");
   const int c4 = lane & 7;
   const int rsub = lane >> 3;
   // phase 1: thread = row; 8 x STS.128, chunk position XOR-swizzled by the row
@@ -144,7 +147,15 @@ __device__ __forceinline__ void epi_store_normal(const GemmParams& p, const uint
       o.x = res[it].x + o.x; o.y = res[it].y + o.y; o.z = res[it].z + o.z; o.w = res[it].w + o.w;
     }
     if (okmask & (1u << it)) {
-      if (kBf16) {
+      if (kSplit3) {
+        uint2 hi, lo;
+        pack_split2(o.x, o.y, hi.x, lo.x);
+        pack_split2(o.z, o.w, hi.y, lo.y);
+        uint8_t* dst = obase + ooff[it] * 2;
+        *reinterpret_cast<uint2*>(dst) = hi;
+        *reinterpret_cast<uint2*>(dst + static_cast<long long>(p.N) * 2) = lo;
+        *reinterpret_cast<uint2*>(dst + static_cast<long long>(p.N) * 4) = hi;
+      } else if (kBf16) {
         uint2 pk;
         pk.x = pack_bf16(o.x, o.y);
         pk.y = pack_bf16(o.z, o.w);
@@ -166,6 +177,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr bool kBf16 = (EPI & EPI_BF16) != 0;
   constexpr bool kPartial = (EPI & EPI_PARTIAL) != 0;
   constexpr int kAct = (EPI >> EPI_ACT_SHIFT) & 3;
+  constexpr bool kSplit3 = (EPI & EPI_SPLIT3) != 0;
   if (p.pdl) griddep_launch_early();
   if (p.pdl) tl_mark(100000 + 1000 + static_cast<int>(gridDim.x));
   // `skip` (decode finished) only changes between steps, which are separated by full dependencies
@@ -372,6 +384,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 } else {
                   for (int e = 0; e < 4; ++e)
                     if (f0 + e < p.M) dst[e] = v[e];
+                }
+              } else if (kSplit3) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[0]) + off;
+                for (int e = 0; e < 4; ++e) {
+                  if (f0 + e < p.M) {
+                    __nv_bfloat16 hi, lo;
+                    split_bf16(v[e], hi, lo);
+                    dst[e] = hi; dst[p.M + e] = lo; dst[2 * p.M + e] = hi;
+                  }
                 }
               } else if (kBf16) {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[0]) + off;

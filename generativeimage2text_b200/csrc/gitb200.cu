@@ -28,6 +28,7 @@
 
 #include "../../include/gitb200.h"
 #include "attention.cuh"
+#include "decode_mega.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "preproc.cuh"
@@ -80,6 +81,7 @@ struct EncLayer {
 };
 struct DecLayer {
   DevBuf wqkv, bqkv, wo, bo, lnag, lnab, w1, b1, w2, b2, lnog, lnob;
+  DevBuf m_wqkv, m_wo, m_w1, m_w2;   // fragment-packed 8-feature tiles for decode_mega_kernel (built by finalize_weights)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -109,6 +111,16 @@ struct gitb200_engine {
   bool use_pdl = true;
   bool use_chain = true;
   bool use_2cta = true;   // encoder / prefill GEMMs through the cta_group::2 kernel (gemm2.cuh)
+  // fp32-grade parity mode: every GEMM operand is a (hi, lo) bf16 pair and each GEMM computes a_hi w_hi + a_lo w_hi +
+  // a_hi w_lo in ONE pass of the same tcgen05 kernel (activations stored [hi | lo | hi], weights [hi | hi | lo] along K);
+  // attention, K/V caches and q/k/v stay fp32; exact QuickGELU.  ~3x the GEMM work: a verification mode (the north star's
+  // "logits within 1e-3" against the fp32 reference), not a serving mode.  Weights must be (re-)uploaded after switching.
+  bool use_mega = true;   // greedy decode steps of <= 64 sequences through the persistent decode_mega_kernel
+  bool mega_coop = true;  // ... launched cooperatively (co-residency of its 148 CTAs guaranteed by the driver)
+  bool mega_ready = false;
+  bool parity = false;
+  int ks() const { return parity ? 3 : 1; }                  // K multiplier of every GEMM operand
+  size_t kvb() const { return parity ? 4 : 2; }              // bytes per K/V cache element
   const gitb200_engine* weights_from = nullptr;   // non-null: weight buffers are borrowed from that engine
 
   // derived geometry
@@ -121,6 +133,7 @@ struct gitb200_engine {
   DevBuf w_patch, cls, pos_emb, lnpre_g, lnpre_b, lnpost_g, lnpost_b;
   std::vector<EncLayer> enc;
   DevBuf w_vp, b_vp, lnvp_g, lnvp_b, words_f32, words_bf16, positions, lnemb_g, lnemb_b, out_bias, temb;
+  DevBuf m_lm;                                              // packed LM-head tiles (decode_mega_kernel)
   std::vector<DecLayer> dec;
   std::set<std::string> seen;
   bool finalized = false;
@@ -130,6 +143,7 @@ struct gitb200_engine {
   DevBuf pt, pxd, phd, pq, pctx, pu;                        // prefill
   DevBuf img_kv, txt_kv, src_row[2];                        // caches
   DevBuf xd_t, hd_t, qkv_t, ctx_t, t_t, u_t, logits;        // decode step
+  DevBuf y_t, qb_t, mega_bar;                               // decode_mega_kernel: pre-LN sums, bf16 q, grid-barrier counters
   DevBuf state, next_token, logprob_sum, tokens_i64, stage_img, stage_tok, stage_lp, prefix_dev;
   DevBuf beam_ws;                                           // beam-search bookkeeping (search.cuh)
   DevBuf sel_ws;                                            // greedy selection partials
@@ -333,7 +347,18 @@ static int launch_gemm2_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st
 template <int BN>
 static int launch_gemm_bn(gitb200_engine* h, const GemmCall& c, cudaStream_t st) {
   const GemmParams& p = c.p;
-  const int code = epi_code(p.transposed != 0, p.out_bf16 != 0, p.resid != nullptr, p.partial != 0, p.act);
+  const int code = epi_code(p.transposed != 0, p.out_bf16 != 0, p.resid != nullptr, p.partial != 0, p.act) | (p.split3 ? EPI_SPLIT3 : 0);
+  if constexpr (BN == 256) {   // parity mode: bf16 outputs that feed another GEMM leave as [hi | lo | hi]
+    switch (code) {
+      case epi_code(false, true, false, false, ACT_QUICKGELU_EXACT) | EPI_SPLIT3: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_QUICKGELU_EXACT) | EPI_SPLIT3>(h, c, st);
+      case epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_SPLIT3: return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_GELU_ERF) | EPI_SPLIT3>(h, c, st);
+      default: break;
+    }
+  }
+  if constexpr (BN == 64 || BN == 128 || BN == 256) {
+    if (code == (epi_code(true, true, false, false, ACT_GELU_ERF) | EPI_SPLIT3))
+      return launch_gemm_inst<BN, epi_code(true, true, false, false, ACT_GELU_ERF) | EPI_SPLIT3>(h, c, st);
+  }
   if constexpr (BN == 192 || BN == 256 || BN == 128) {
     switch (code) {
       case epi_code(false, true, false, false, ACT_NONE): return launch_gemm_inst<BN, epi_code(false, true, false, false, ACT_NONE)>(h, c, st);
@@ -389,10 +414,11 @@ static int launch_gemm(gitb200_engine* h, GemmCall c, cudaStream_t st) {
   if (p.k_splits > 1 && !p.partial) return fail(h, "gemm: k_splits > 1 needs the partial-sum epilogue");
   if (p.partial && p.split_stride < static_cast<long long>(p.N) * p.ldo) return fail(h, "gemm: split_stride smaller than one partial buffer");
   int bn = c.bn > 0 ? c.bn : pick_bn(h, p.M, p.N, p.transposed != 0);
+  if (p.split3 && !p.transposed) bn = 256;
   // 2-CTA (cta_group::2) kernel: explicit request (bn = 1000 + BN, unit tests) or engine option for the big GEMMs
   // Measured (tools/gemm_sweep.py, M = 12608): pairs win on wide outputs (+7-10 %) and on K = 3072 (+11 %); the
   // K = N = 768 out-projection is epilogue bound and stays on 1-CTA 128x192 tiles.
-  if (bn < 1000 && h->use_2cta && !p.transposed && p.k_splits == 1 && p.M >= 2048) {
+  if (bn < 1000 && h->use_2cta && !h->parity && !p.transposed && p.k_splits == 1 && p.M >= 2048) {
     if (p.N % 256 == 0 && p.N >= 1024) bn = 1256;
     else if (p.N % 192 == 0 && p.K >= 1536) bn = 1192;
   }
@@ -488,6 +514,20 @@ static int launch_attention(gitb200_engine* h, const AttnParams& ap, cudaStream_
   return 0;
 }
 
+static int launch_attention_f32(gitb200_engine* h, const AttnF32Params& p, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(4) * (64 + p.S) * sizeof(float);
+  if (smem > 200 * 1024) return fail(h, "parity attention: %d keys do not fit in shared memory", p.S);
+  static size_t attr_done[64] = {0};
+  if (attr_done[h->device & 63] < smem) {
+    CK(cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done[h->device & 63] = smem;
+  }
+  const long long items = static_cast<long long>(p.B) * p.H * p.S;
+  attn_f32_kernel<<<static_cast<unsigned int>((items + 3) / 4), 128, smem, st>>>(p);
+  CKL(h, "attn_f32_kernel");
+  return 0;
+}
+
 __global__ void cvt_rows_kernel(const float* __restrict__ src, long long src_ld, bf16* __restrict__ dst, long long dst_ld,
                                 long long rows, long long cols, long long dst_cols) {
   const long long total = rows * dst_cols;
@@ -495,6 +535,19 @@ __global__ void cvt_rows_kernel(const float* __restrict__ src, long long src_ld,
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / dst_cols, c = i - r * dst_cols;
     dst[r * dst_ld + c] = __float2bfloat16_rn(c < cols ? src[r * src_ld + c] : 0.0f);
+  }
+}
+// parity mode weights: [rows, 3 * dst_cols] = [hi | hi | lo]
+__global__ void cvt_rows_split3_kernel(const float* __restrict__ src, long long src_ld, bf16* __restrict__ dst, long long rows,
+                                       long long cols, long long dst_cols) {
+  const long long total = rows * dst_cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / dst_cols, c = i - r * dst_cols;
+    bf16 hi, lo;
+    split_bf16(c < cols ? src[r * src_ld + c] : 0.0f, hi, lo);
+    bf16* d = dst + r * 3 * dst_cols + c;
+    d[0] = hi; d[dst_cols] = hi; d[2 * dst_cols] = lo;
   }
 }
 __global__ void sum_partials_kernel(const float* __restrict__ parts, float* __restrict__ out, long long n, int splits) {
@@ -542,6 +595,13 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (strcmp(name, "use_pdl") == 0) { h->use_pdl = value != 0; return 0; }
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
   if (strcmp(name, "use_2cta") == 0) { h->use_2cta = value != 0; return 0; }
+  if (strcmp(name, "use_mega") == 0) { h->use_mega = value != 0; return 0; }
+  if (strcmp(name, "mega_coop") == 0) { h->mega_coop = value != 0; return 0; }
+  if (strcmp(name, "parity") == 0) {
+    if (h->weights_from != nullptr) return fail(h, "parity: this engine borrows its weights; switch the owning engine");
+    if (h->parity != (value != 0)) { h->parity = value != 0; h->finalized = false; h->seen.clear(); h->tmaps.clear(); }
+    return 0;
+  }
   return fail(h, "unknown option %s", name);
 }
 
@@ -601,7 +661,7 @@ extern "C" int gitb200_create(const gitb200_config* cfg, int device, gitb200_eng
 static void release_all(gitb200_engine* h) {
   DevBuf* bufs[] = {&h->w_patch, &h->cls, &h->pos_emb, &h->lnpre_g, &h->lnpre_b, &h->lnpost_g, &h->lnpost_b, &h->w_vp,
                     &h->b_vp, &h->lnvp_g, &h->lnvp_b, &h->words_f32, &h->words_bf16, &h->positions, &h->lnemb_g,
-                    &h->lnemb_b, &h->out_bias, &h->temb, &h->x, &h->h, &h->qkv, &h->ctx, &h->u, &h->feats, &h->feats_f32, &h->pos_interp,
+                    &h->lnemb_b, &h->out_bias, &h->temb, &h->m_lm, &h->y_t, &h->qb_t, &h->mega_bar, &h->x, &h->h, &h->qkv, &h->ctx, &h->u, &h->feats, &h->feats_f32, &h->pos_interp,
                     &h->pt, &h->pxd, &h->phd, &h->pq, &h->pctx, &h->pu, &h->img_kv, &h->txt_kv, &h->src_row[0],
                     &h->src_row[1], &h->xd_t, &h->hd_t, &h->qkv_t, &h->ctx_t, &h->t_t, &h->u_t, &h->logits, &h->state,
                     &h->next_token, &h->logprob_sum, &h->tokens_i64, &h->stage_img, &h->stage_tok, &h->stage_lp,
@@ -612,7 +672,8 @@ static void release_all(gitb200_engine* h) {
     for (DevBuf* b : lb) b->release();
   }
   for (auto& l : h->dec) {
-    DevBuf* lb[] = {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.lnag, &l.lnab, &l.w1, &l.b1, &l.w2, &l.b2, &l.lnog, &l.lnob};
+    DevBuf* lb[] = {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.lnag, &l.lnab, &l.w1, &l.b1, &l.w2, &l.b2, &l.lnog, &l.lnob,
+                    &l.m_wqkv, &l.m_wo, &l.m_w1, &l.m_w2};
     for (DevBuf* b : lb) b->release();
   }
 }
@@ -621,11 +682,12 @@ static void release_all(gitb200_engine* h) {
 static std::vector<DevBuf*> weight_bufs(gitb200_engine* h) {
   std::vector<DevBuf*> v = {&h->w_patch, &h->cls, &h->pos_emb, &h->lnpre_g, &h->lnpre_b, &h->lnpost_g, &h->lnpost_b, &h->w_vp,
                             &h->b_vp, &h->lnvp_g, &h->lnvp_b, &h->words_f32, &h->words_bf16, &h->positions, &h->lnemb_g,
-                            &h->lnemb_b, &h->out_bias, &h->temb};
+                            &h->lnemb_b, &h->out_bias, &h->temb, &h->m_lm};
   for (auto& l : h->enc)
     for (DevBuf* b : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.ln1g, &l.ln1b, &l.ln2g, &l.ln2b, &l.w1, &l.b1, &l.w2, &l.b2}) v.push_back(b);
   for (auto& l : h->dec)
-    for (DevBuf* b : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.lnag, &l.lnab, &l.w1, &l.b1, &l.w2, &l.b2, &l.lnog, &l.lnob}) v.push_back(b);
+    for (DevBuf* b : {&l.wqkv, &l.bqkv, &l.wo, &l.bo, &l.lnag, &l.lnab, &l.w1, &l.b1, &l.w2, &l.b2, &l.lnog, &l.lnob,
+                      &l.m_wqkv, &l.m_wo, &l.m_w1, &l.m_w2}) v.push_back(b);
   return v;
 }
 
@@ -642,6 +704,8 @@ extern "C" int gitb200_share_weights(gitb200_engine* h, gitb200_engine* src) {
   h->tmaps.clear();
   drop_step_graphs(h);
   h->seen = src->seen;
+  h->parity = src->parity;
+  h->mega_ready = src->mega_ready;
   h->finalized = true;
   h->weights_from = src;
   return 0;
@@ -670,12 +734,11 @@ static int store_f32(gitb200_engine* h, DevBuf& dst, size_t total_elems, size_t 
 }
 static int store_bf16(gitb200_engine* h, DevBuf& dst, long long total_rows, long long dst_cols, long long row_off,
                       const float* src, long long rows, long long cols, cudaStream_t st) {
-  const bool fresh = dst.p == nullptr;
-  CK(dst.ensure(static_cast<size_t>(total_rows) * dst_cols * sizeof(bf16)));
-  (void)fresh;
+  CK(dst.ensure(static_cast<size_t>(total_rows) * dst_cols * h->ks() * sizeof(bf16)));
   const long long total = rows * dst_cols;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  cvt_rows_kernel<<<grid, 256, 0, st>>>(src, cols, dst.as<bf16>() + row_off * dst_cols, dst_cols, rows, cols, dst_cols);
+  if (h->parity) cvt_rows_split3_kernel<<<grid, 256, 0, st>>>(src, cols, dst.as<bf16>() + row_off * 3 * dst_cols, rows, cols, dst_cols);
+  else cvt_rows_kernel<<<grid, 256, 0, st>>>(src, cols, dst.as<bf16>() + row_off * dst_cols, dst_cols, rows, cols, dst_cols);
   CKL(h, "cvt_rows_kernel");
   return 0;
 }
@@ -815,6 +878,27 @@ extern "C" int gitb200_finalize_weights(gitb200_engine* h, void* stream) {
   for (int f = 0; f < h->cfg.num_frames_emb; ++f) need.push_back("img_temperal_embedding." + std::to_string(f));
   for (const std::string& k : need)
     if (!h->seen.count(k)) return fail(h, "finalize_weights: missing tensor %s", k.c_str());
+  // fragment-packed weight tiles of the persistent decode-step kernel (decode_mega.cuh)
+  h->mega_ready = false;
+  if (!h->parity && h->D == kMegaD && h->F == kMegaF && h->cfg.dec_heads == kMegaH && h->cfg.dec_layers <= 6) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto pack = [&](DevBuf& dst, const DevBuf& src, long long ldw, int n_feat, int k0, long long n_tiles, int stride, int offset) -> int {
+      CK(dst.ensure(static_cast<size_t>(n_tiles) * stride * kMegaTileBytes));
+      const long long total = n_tiles * 48 * 32;
+      pack_tiles_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
+          src.as<bf16>(), ldw, n_feat, k0, dst.as<uint8_t>(), n_tiles, stride, offset);
+      CKL(h, "pack_tiles_kernel");
+      return 0;
+    };
+    for (auto& l : h->dec) {
+      TRY(pack(l.m_wqkv, l.wqkv, h->D, 3 * h->D, 0, 3 * h->D / 8, 1, 0));
+      TRY(pack(l.m_wo, l.wo, h->D, h->D, 0, h->D / 8, 1, 0));
+      TRY(pack(l.m_w1, l.w1, h->D, h->F, 0, h->F / 8, 1, 0));
+      for (int sl = 0; sl < 4; ++sl) TRY(pack(l.m_w2, l.w2, h->F, h->D, sl * kMegaD, h->D / 8, 4, sl));
+    }
+    TRY(pack(h->m_lm, h->words_bf16, h->D, h->V, 0, (h->V + 7) / 8, 1, 0));
+    h->mega_ready = true;
+  }
   CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   CK(cudaGetLastError());
   h->finalized = true;
@@ -835,12 +919,14 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
   const int d = h->d, L = h->Lc, gh = h->gh, gw = h->gw, Kp = h->Kp, H = h->cfg.enc_heads;
   const int NI = B * frames;
   const long long Me = static_cast<long long>(NI) * L;
+  const int ks = h->ks();                 // parity mode: GEMM operands are [hi | lo | hi] -> 3x the K extent
+  const bool par = h->parity;
   CK(h->x.ensure(Me * d * 4));
-  CK(h->h.ensure(Me * d * 2));
-  CK(h->qkv.ensure(Me * 3 * d * 2));
-  CK(h->ctx.ensure(Me * d * 2));
-  CK(h->u.ensure(std::max<long long>(Me * 4 * d * 2, static_cast<long long>(NI) * gh * gw * Kp * 2)));
-  CK(h->feats.ensure(Me * d * 2));
+  CK(h->h.ensure(Me * d * 2 * ks));
+  CK(h->qkv.ensure(Me * 3 * d * (par ? 4 : 2)));         // parity: q | k | v stay fp32
+  CK(h->ctx.ensure(Me * d * 2 * ks));
+  CK(h->u.ensure(std::max<long long>(Me * 4 * d * 2, static_cast<long long>(NI) * gh * gw * Kp * 2) * ks));
+  CK(h->feats.ensure(Me * d * 2 * ks));
   float* x = h->x.as<float>();
   bf16* hb = h->h.as<bf16>();
   bf16* qkv = h->qkv.as<bf16>();
@@ -862,9 +948,9 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
   {
     const long long total = static_cast<long long>(NI) * gh * gw * (Kp / 8);
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->num_sms * 16));
-    im2col_patch_kernel<<<grid, 256, 0, st>>>(images, u, NI, h->in_h, h->in_w, h->cfg.patch, gh, gw, Kp);
+    im2col_patch_kernel<<<grid, 256, 0, st>>>(images, u, NI, h->in_h, h->in_w, h->cfg.patch, gh, gw, Kp, par ? 1 : 0);
     CKL(h, "im2col_patch_kernel");
-    GemmCall c = gemm_plain(u, Kp, h->w_patch.as<bf16>(), Kp, NI * gh * gw, d, Kp, nullptr, ACT_NONE, nullptr, x, false);
+    GemmCall c = gemm_plain(u, Kp * ks, h->w_patch.as<bf16>(), Kp * ks, NI * gh * gw, d, Kp * ks, nullptr, ACT_NONE, nullptr, x, false);
     c.p.rows_per_batch = gh * gw;
     c.p.batch_stride = L;
     c.p.row_offset = 1;
@@ -876,20 +962,40 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
       cls_pos_lnpre_kernel<1024><<<gridr, 256, 0, st>>>(x, h->cls.as<float>(), pos, h->lnpre_g.as<float>(), h->lnpre_b.as<float>(), static_cast<int>(Me), L);
     CKL(h, "cls_pos_lnpre_kernel");
   }
+  auto ln_enc = [&](const float* g, const float* b) {
+    LnParams p = ln_params(x, nullptr, nullptr, g, b, 1e-5f, nullptr, hb, static_cast<int>(Me));
+    p.split3 = par ? 1 : 0;
+    return p;
+  };
   for (int i = 0; i < h->cfg.enc_layers; ++i) {
     EncLayer& l = h->enc[i];
-    TRY(launch_ln(h, ln_params(x, nullptr, nullptr, l.ln1g.as<float>(), l.ln1b.as<float>(), 1e-5f, nullptr, hb, static_cast<int>(Me)), d, st));
-    TRY(launch_gemm(h, gemm_plain(hb, d, l.wqkv.as<bf16>(), d, static_cast<int>(Me), 3 * d, d, l.bqkv.as<float>(), ACT_NONE, nullptr, qkv, true), st));
-    AttnParams ap{};
-    ap.q = qkv; ap.k = qkv + d; ap.v = qkv + 2 * d; ap.out = ctx;
-    ap.B = NI; ap.S = L; ap.H = H;
-    ap.q_rs = 3 * d; ap.kv_rs = 3 * d; ap.q_bs = static_cast<long long>(L) * 3 * d; ap.kv_bs = ap.q_bs;
-    ap.o_rs = d; ap.o_bs = static_cast<long long>(L) * d;
-    TRY(launch_attention(h, ap, st));
-    TRY(launch_gemm(h, gemm_plain(ctx, d, l.wo.as<bf16>(), d, static_cast<int>(Me), d, d, l.bo.as<float>(), ACT_NONE, x, x, false), st));
-    TRY(launch_ln(h, ln_params(x, nullptr, nullptr, l.ln2g.as<float>(), l.ln2b.as<float>(), 1e-5f, nullptr, hb, static_cast<int>(Me)), d, st));
-    TRY(launch_gemm(h, gemm_plain(hb, d, l.w1.as<bf16>(), d, static_cast<int>(Me), 4 * d, d, l.b1.as<float>(), ACT_QUICKGELU, nullptr, u, true), st));
-    TRY(launch_gemm(h, gemm_plain(u, 4 * d, l.w2.as<bf16>(), 4 * d, static_cast<int>(Me), d, 4 * d, l.b2.as<float>(), ACT_NONE, x, x, false), st));
+    TRY(launch_ln(h, ln_enc(l.ln1g.as<float>(), l.ln1b.as<float>()), d, st));
+    TRY(launch_gemm(h, gemm_plain(hb, d * ks, l.wqkv.as<bf16>(), d * ks, static_cast<int>(Me), 3 * d, d * ks, l.bqkv.as<float>(), ACT_NONE, nullptr, qkv, !par), st));
+    if (par) {
+      AttnF32Params ap{};
+      const float* qf = h->qkv.as<float>();
+      ap.q = qf; ap.k = qf + d; ap.v = qf + 2 * d; ap.out = ctx;
+      ap.B = NI; ap.S = L; ap.H = H; ap.d_model = d;
+      ap.q_rs = 3 * d; ap.kv_rs = 3 * d; ap.q_bs = static_cast<long long>(L) * 3 * d; ap.kv_bs = ap.q_bs;
+      ap.o_bs = static_cast<long long>(L) * 3 * d;
+      TRY(launch_attention_f32(h, ap, st));
+    } else {
+      AttnParams ap{};
+      ap.q = qkv; ap.k = qkv + d; ap.v = qkv + 2 * d; ap.out = ctx;
+      ap.B = NI; ap.S = L; ap.H = H;
+      ap.q_rs = 3 * d; ap.kv_rs = 3 * d; ap.q_bs = static_cast<long long>(L) * 3 * d; ap.kv_bs = ap.q_bs;
+      ap.o_rs = d; ap.o_bs = static_cast<long long>(L) * d;
+      TRY(launch_attention(h, ap, st));
+    }
+    TRY(launch_gemm(h, gemm_plain(ctx, d * ks, l.wo.as<bf16>(), d * ks, static_cast<int>(Me), d, d * ks, l.bo.as<float>(), ACT_NONE, x, x, false), st));
+    TRY(launch_ln(h, ln_enc(l.ln2g.as<float>(), l.ln2b.as<float>()), d, st));
+    {
+      GemmCall c = gemm_plain(hb, d * ks, l.w1.as<bf16>(), d * ks, static_cast<int>(Me), 4 * d, d * ks, l.b1.as<float>(),
+                              par ? ACT_QUICKGELU_EXACT : ACT_QUICKGELU, nullptr, u, true);
+      if (par) { c.p.split3 = 1; c.p.ldo = 3LL * 4 * d; }
+      TRY(launch_gemm(h, c, st));
+    }
+    TRY(launch_gemm(h, gemm_plain(u, 4 * d * ks, l.w2.as<bf16>(), 4 * d * ks, static_cast<int>(Me), d, 4 * d * ks, l.b2.as<float>(), ACT_NONE, x, x, false), st));
   }
   // ln_post on all tokens (+ temporal embedding), re-ordered to [B, frames*L, d]
   {
@@ -897,6 +1003,7 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
     p.remap_B = B; p.remap_F = frames; p.remap_L = L;
     // temporal embeddings only for list inputs (reference layers/decoder.py:846-849; a bare tensor skips them)
     p.temb = (list_input && h->cfg.num_frames_emb > 0) ? h->temb.as<float>() : nullptr;
+    p.split3 = par ? 1 : 0;
     TRY(launch_ln(h, p, d, st));
   }
   h->cur_B = B;
@@ -913,13 +1020,14 @@ static int encode_impl(gitb200_engine* h, const float* images, int B, int frames
 // stores its own partial-sum buffer; the consumer (decode attention / LayerNorm) adds them in split order.
 constexpr int kQkvSplits = 3, kOutProjSplits = 6, kFc2Splits = 8, kMaxProjSplits = 8;
 
-static bf16* img_kv_ptr(gitb200_engine* h, int layer, int kv) {
+// K/V caches: bf16, or fp32 in parity mode (void*: the element size is the engine's kvb())
+static char* img_kv_ptr(gitb200_engine* h, int layer, int kv, long long elem_off = 0) {
   const long long per = static_cast<long long>(h->cur_B) * h->cur_M * h->D;
-  return h->img_kv.as<bf16>() + (static_cast<long long>(layer) * 2 + kv) * per;
+  return h->img_kv.as<char>() + ((static_cast<long long>(layer) * 2 + kv) * per + elem_off) * h->kvb();
 }
-static bf16* txt_kv_ptr(gitb200_engine* h, int layer, int kv) {
+static char* txt_kv_ptr(gitb200_engine* h, int layer, int kv, long long elem_off = 0) {
   const long long per = static_cast<long long>(h->cur_rows) * h->T_alloc * h->D;
-  return h->txt_kv.as<bf16>() + (static_cast<long long>(layer) * 2 + kv) * per;
+  return h->txt_kv.as<char>() + ((static_cast<long long>(layer) * 2 + kv) * per + elem_off) * h->kvb();
 }
 
 static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* vproj_out, cudaStream_t st) {
@@ -927,24 +1035,30 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
   const int D = h->D, F = h->F, d = h->d, M = h->cur_M, nl = h->cfg.dec_layers, H = h->cfg.dec_heads;
   const long long rows = static_cast<long long>(B) * M;
   const int R = B * beam;
+  const int ks = h->ks();
+  const bool par = h->parity;
+  const long long kvb = static_cast<long long>(h->kvb());
   CK(h->pt.ensure(rows * D * 4));
   CK(h->pxd.ensure(rows * D * 4));
-  CK(h->phd.ensure(rows * D * 2));
-  CK(h->pq.ensure(rows * D * 2));
-  CK(h->pctx.ensure(rows * D * 2));
-  CK(h->pu.ensure(rows * F * 2));
-  CK(h->img_kv.ensure(static_cast<long long>(nl) * 2 * rows * D * 2));
-  CK(h->txt_kv.ensure(static_cast<long long>(nl) * 2 * R * T_alloc * D * 2));
+  CK(h->phd.ensure(rows * D * 2 * ks));
+  CK(h->pq.ensure(rows * D * kvb));
+  CK(h->pctx.ensure(rows * D * 2 * ks));
+  CK(h->pu.ensure(rows * F * 2 * ks));
+  CK(h->img_kv.ensure(static_cast<long long>(nl) * 2 * rows * D * kvb));
+  CK(h->txt_kv.ensure(static_cast<long long>(nl) * 2 * R * T_alloc * D * kvb));
   CK(h->src_row[0].ensure(static_cast<size_t>(R) * T_alloc * 4));
   CK(h->src_row[1].ensure(static_cast<size_t>(R) * T_alloc * 4));
   CK(h->xd_t.ensure(static_cast<size_t>(R) * D * 4));
-  CK(h->hd_t.ensure(static_cast<size_t>(R) * D * 2));
+  CK(h->hd_t.ensure(static_cast<size_t>(R) * D * 2 * ks));
   CK(h->qkv_t.ensure(static_cast<size_t>(kQkvSplits) * R * 3 * D * 4));   // split-K partial-sum buffers
-  CK(h->ctx_t.ensure(static_cast<size_t>(R) * D * 2));
+  CK(h->ctx_t.ensure(static_cast<size_t>(R) * D * 2 * ks));
   CK(h->t_t.ensure(static_cast<size_t>(kMaxProjSplits) * R * D * 4));
-  CK(h->u_t.ensure(static_cast<size_t>(R) * F * 2));
+  CK(h->u_t.ensure(static_cast<size_t>(R) * F * 2 * ks));
   CK(h->logits.ensure(static_cast<size_t>(R) * h->V * 4));
-  CK(h->state.ensure(sizeof(StepState)));
+  CK(h->state.ensure(sizeof(StepState) + 64));            // + the megakernel's error word
+  CK(h->y_t.ensure(static_cast<size_t>(R) * D * 4));
+  CK(h->qb_t.ensure(static_cast<size_t>(R) * D * 2));
+  CK(h->mega_bar.ensure(64));
   CK(h->next_token.ensure(static_cast<size_t>(R) * 8));
   CK(h->logprob_sum.ensure(static_cast<size_t>(R) * 4));
   h->cur_beam = beam;
@@ -957,32 +1071,47 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
   bf16* ctx = h->pctx.as<bf16>();
   bf16* u = h->pu.as<bf16>();
 
+  auto ln_pre = [&](const float* g, const float* b, float eps) {
+    LnParams p = ln_params(t, nullptr, nullptr, g, b, eps, xd, hd, static_cast<int>(rows));
+    p.split3 = par ? 1 : 0;
+    return p;
+  };
   // visual projection: Linear(dv -> 768) + LayerNorm(1e-5)
-  TRY(launch_gemm(h, gemm_plain(h->feats.as<bf16>(), d, h->w_vp.as<bf16>(), d, static_cast<int>(rows), D, d, h->b_vp.as<float>(), ACT_NONE, nullptr, t, false), st));
-  {
-    LnParams p = ln_params(t, nullptr, nullptr, h->lnvp_g.as<float>(), h->lnvp_b.as<float>(), 1e-5f, xd, hd, static_cast<int>(rows));
-    TRY(launch_ln(h, p, D, st));
-    if (vproj_out) CK(cudaMemcpyAsync(vproj_out, xd, rows * D * 4, cudaMemcpyDeviceToDevice, st));
-  }
+  TRY(launch_gemm(h, gemm_plain(h->feats.as<bf16>(), d * ks, h->w_vp.as<bf16>(), d * ks, static_cast<int>(rows), D, d * ks, h->b_vp.as<float>(), ACT_NONE, nullptr, t, false), st));
+  TRY(launch_ln(h, ln_pre(h->lnvp_g.as<float>(), h->lnvp_b.as<float>(), 1e-5f), D, st));
+  if (vproj_out) CK(cudaMemcpyAsync(vproj_out, xd, rows * D * 4, cudaMemcpyDeviceToDevice, st));
   for (int j = 0; j < nl; ++j) {
     DecLayer& l = h->dec[j];
-    // fused q|k|v projection; k and v rows go straight into the image K/V cache
-    GemmCall c = gemm_plain(hd, D, l.wqkv.as<bf16>(), D, static_cast<int>(rows), 3 * D, D, l.bqkv.as<float>(), ACT_NONE, nullptr, q, true);
+    // fused q|k|v projection; k and v rows go straight into the image K/V cache (bf16; fp32 in parity mode)
+    GemmCall c = gemm_plain(hd, D * ks, l.wqkv.as<bf16>(), D * ks, static_cast<int>(rows), 3 * D, D * ks, l.bqkv.as<float>(), ACT_NONE, nullptr, q, !par);
     c.p.seg_n = D;
     c.p.out[0] = q; c.p.out[1] = img_kv_ptr(h, j, 0); c.p.out[2] = img_kv_ptr(h, j, 1);
     c.p.ldo = D;
     TRY(launch_gemm(h, c, st));
     if (j + 1 == nl) break;  // image rows of the last layer are never read (text rows only need their K/V)
-    AttnParams ap{};
-    ap.q = q; ap.k = img_kv_ptr(h, j, 0); ap.v = img_kv_ptr(h, j, 1); ap.out = ctx;
-    ap.B = B; ap.S = M; ap.H = H;
-    ap.q_rs = D; ap.kv_rs = D; ap.q_bs = static_cast<long long>(M) * D; ap.kv_bs = ap.q_bs; ap.o_rs = D; ap.o_bs = ap.q_bs;
-    TRY(launch_attention(h, ap, st));
-    TRY(launch_gemm(h, gemm_plain(ctx, D, l.wo.as<bf16>(), D, static_cast<int>(rows), D, D, l.bo.as<float>(), ACT_NONE, xd, t, false), st));
-    TRY(launch_ln(h, ln_params(t, nullptr, nullptr, l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f, xd, hd, static_cast<int>(rows)), D, st));
-    TRY(launch_gemm(h, gemm_plain(hd, D, l.w1.as<bf16>(), D, static_cast<int>(rows), F, D, l.b1.as<float>(), ACT_GELU_ERF, nullptr, u, true), st));
-    TRY(launch_gemm(h, gemm_plain(u, F, l.w2.as<bf16>(), F, static_cast<int>(rows), D, F, l.b2.as<float>(), ACT_NONE, xd, t, false), st));
-    TRY(launch_ln(h, ln_params(t, nullptr, nullptr, l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f, xd, hd, static_cast<int>(rows)), D, st));
+    if (par) {
+      AttnF32Params ap{};
+      ap.q = h->pq.as<float>(); ap.k = reinterpret_cast<const float*>(img_kv_ptr(h, j, 0));
+      ap.v = reinterpret_cast<const float*>(img_kv_ptr(h, j, 1)); ap.out = ctx;
+      ap.B = B; ap.S = M; ap.H = H; ap.d_model = D;
+      ap.q_rs = D; ap.kv_rs = D; ap.q_bs = static_cast<long long>(M) * D; ap.kv_bs = ap.q_bs; ap.o_bs = 3 * ap.q_bs;
+      TRY(launch_attention_f32(h, ap, st));
+    } else {
+      AttnParams ap{};
+      ap.q = q; ap.k = reinterpret_cast<const bf16*>(img_kv_ptr(h, j, 0)); ap.v = reinterpret_cast<const bf16*>(img_kv_ptr(h, j, 1)); ap.out = ctx;
+      ap.B = B; ap.S = M; ap.H = H;
+      ap.q_rs = D; ap.kv_rs = D; ap.q_bs = static_cast<long long>(M) * D; ap.kv_bs = ap.q_bs; ap.o_rs = D; ap.o_bs = ap.q_bs;
+      TRY(launch_attention(h, ap, st));
+    }
+    TRY(launch_gemm(h, gemm_plain(ctx, D * ks, l.wo.as<bf16>(), D * ks, static_cast<int>(rows), D, D * ks, l.bo.as<float>(), ACT_NONE, xd, t, false), st));
+    TRY(launch_ln(h, ln_pre(l.lnag.as<float>(), l.lnab.as<float>(), 1e-12f), D, st));
+    {
+      GemmCall c1 = gemm_plain(hd, D * ks, l.w1.as<bf16>(), D * ks, static_cast<int>(rows), F, D * ks, l.b1.as<float>(), ACT_GELU_ERF, nullptr, u, true);
+      if (par) { c1.p.split3 = 1; c1.p.ldo = 3LL * F; }
+      TRY(launch_gemm(h, c1, st));
+    }
+    TRY(launch_gemm(h, gemm_plain(u, F * ks, l.w2.as<bf16>(), F * ks, static_cast<int>(rows), D, F * ks, l.b2.as<float>(), ACT_NONE, xd, t, false), st));
+    TRY(launch_ln(h, ln_pre(l.lnog.as<float>(), l.lnob.as<float>(), 1e-12f), D, st));
   }
   return 0;
 }
@@ -995,16 +1124,15 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
   cudaStream_t st = ln_.st;
   StepState* state = h->state.as<StepState>();
   const int* skip = &state->finished;
-  const long long r0 = ln_.row0;
-  float* xd = h->xd_t.as<float>() + r0 * D;
-  bf16* hd = h->hd_t.as<bf16>() + r0 * D;
-  float* qkv = h->qkv_t.as<float>() + r0 * 3 * D;
-  bf16* ctx = h->ctx_t.as<bf16>() + r0 * D;
-  float* t = h->t_t.as<float>() + r0 * D;
-  bf16* u = h->u_t.as<bf16>() + r0 * F;
-  float* logits = h->logits.as<float>() + r0 * h->V;
-  const long long img_off = static_cast<long long>(ln_.b0) * h->cur_M * D;
-  const long long txt_off = r0 * h->T_alloc * D;
+  const int ks = h->ks();
+  const bool par = h->parity;
+  float* xd = h->xd_t.as<float>();
+  bf16* hd = h->hd_t.as<bf16>();
+  float* qkv = h->qkv_t.as<float>();
+  bf16* ctx = h->ctx_t.as<bf16>();
+  float* t = h->t_t.as<float>();
+  bf16* u = h->u_t.as<bf16>();
+  float* logits = h->logits.as<float>();
   const bool pdl = h->use_pdl;
   // Ordering inside the step: flag chain (greedy; the beam bookkeeping kernels still use grid dependencies).
   const bool chain_on = pdl && h->use_chain && beam == 1;
@@ -1019,7 +1147,7 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
   // chain head: launched WITHOUT the PDL attribute -> fully ordered after the previous step
   CK(launch_k(false, embed_ln_kernel<768>, dim3((R + 7) / 8), dim3(256), 0, st, tokens, 1LL, h->words_f32.as<float>(),
               h->positions.as<float>(), h->lnemb_g.as<float>(), h->lnemb_b.as<float>(), xd, hd, R, 0,
-              static_cast<const StepState*>(state), h->V, cs));
+              static_cast<const StepState*>(state), h->V, par ? 1 : 0, cs));
   CKL(h, "embed_ln_kernel");
   next_link((R + 7) / 8);
   // split-K GEMMs write partial-sum buffers; bias / residual / LayerNorm live in the consumer kernel
@@ -1034,6 +1162,7 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
     LnParams p = ln_params(parts, bias, resid, g, b, 1e-12f, of32, obf16, rows);
     p.n_partials = n;
     p.partial_stride = static_cast<long long>(rows) * D;
+    p.split3 = par ? 1 : 0;
     return p;
   };
   auto ln = [&](LnParams p) -> int {
@@ -1044,33 +1173,55 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
   };
   for (int j = 0; j < nl; ++j) {
     DecLayer& l = h->dec[j];
-    TRY(skinny(gemm_skinny(hd, D, l.wqkv.as<bf16>(), D, R, 3 * D, D, nullptr, ACT_NONE, qkv, 3 * D, false, kQkvSplits, skip, pdl)));
-    DecAttnParams ap{};
-    ap.qkv = qkv; ap.n_partials = kQkvSplits; ap.partial_stride = static_cast<long long>(R) * 3 * D;
-    ap.bqkv = l.bqkv.as<float>();
-    ap.img_k = img_kv_ptr(h, j, 0) + img_off; ap.img_v = img_kv_ptr(h, j, 1) + img_off;
-    ap.txt_k = txt_kv_ptr(h, j, 0) + txt_off; ap.txt_v = txt_kv_ptr(h, j, 1) + txt_off;
-    ap.src_row = src_row; ap.ctx = ctx; ap.B = ln_.nb; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
-    ap.state = state;
-    ap.chunk_rows = h->attn_chunk_rows; ap.box_rows = h->attn_box_rows;
-    ap.chain = cs;
-    CUtensorMap tk, tv;
-    TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
-    TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
-    dim3 grid(std::min(h->attn_grid, ln_.nb * h->cfg.dec_heads));
-    if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1, true>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
-    else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
-    else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
-    CKL(h, "decode_attn_kernel");
-    next_link(grid.x);
-    TRY(skinny(gemm_skinny(ctx, D, l.wo.as<bf16>(), D, R, D, D, nullptr, ACT_NONE, t, D, false, kOutProjSplits, skip, pdl)));
+    TRY(skinny(gemm_skinny(hd, D * ks, l.wqkv.as<bf16>(), D * ks, R, 3 * D, D * ks, nullptr, ACT_NONE, qkv, 3 * D, false, kQkvSplits, skip, pdl)));
+    if (par) {
+      DecAttnF32Params ap{};
+      ap.qkv = qkv; ap.n_partials = kQkvSplits; ap.partial_stride = static_cast<long long>(R) * 3 * D;
+      ap.bqkv = l.bqkv.as<float>();
+      ap.img_k = reinterpret_cast<const float*>(img_kv_ptr(h, j, 0)); ap.img_v = reinterpret_cast<const float*>(img_kv_ptr(h, j, 1));
+      ap.txt_k = reinterpret_cast<float*>(txt_kv_ptr(h, j, 0)); ap.txt_v = reinterpret_cast<float*>(txt_kv_ptr(h, j, 1));
+      ap.src_row = src_row; ap.ctx = ctx; ap.R = R; ap.beam = beam; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
+      ap.state = state;
+      ap.chain = cs;
+      const size_t smem = static_cast<size_t>(4) * (192 + h->cur_M + h->T_alloc) * sizeof(float);
+      if (smem > 200 * 1024) return fail(h, "parity decode attention: %d keys do not fit in shared memory", h->cur_M + h->T_alloc);
+      CK(cudaFuncSetAttribute(decode_attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      const unsigned int grid = static_cast<unsigned int>((R * h->cfg.dec_heads + 3) / 4);
+      CK(launch_k(pdl, decode_attn_f32_kernel, dim3(grid), dim3(128), smem, st, ap));
+      CKL(h, "decode_attn_f32_kernel");
+      next_link(grid);
+    } else {
+      DecAttnParams ap{};
+      ap.qkv = qkv; ap.n_partials = kQkvSplits; ap.partial_stride = static_cast<long long>(R) * 3 * D;
+      ap.bqkv = l.bqkv.as<float>();
+      ap.img_k = reinterpret_cast<const bf16*>(img_kv_ptr(h, j, 0)); ap.img_v = reinterpret_cast<const bf16*>(img_kv_ptr(h, j, 1));
+      ap.txt_k = reinterpret_cast<bf16*>(txt_kv_ptr(h, j, 0)); ap.txt_v = reinterpret_cast<bf16*>(txt_kv_ptr(h, j, 1));
+      ap.src_row = src_row; ap.ctx = ctx; ap.B = ln_.nb; ap.M = h->cur_M; ap.T_alloc = h->T_alloc; ap.D = D;
+      ap.state = state;
+      ap.chunk_rows = h->attn_chunk_rows; ap.box_rows = h->attn_box_rows;
+      ap.chain = cs;
+      CUtensorMap tk, tv;
+      TRY(get_tmap(h, ap.img_k, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tk, false));
+      TRY(get_tmap(h, ap.img_v, static_cast<long long>(ln_.nb) * h->cur_M, D, D, ap.box_rows, &tv, false));
+      dim3 grid(std::min(h->attn_grid, ln_.nb * h->cfg.dec_heads));
+      if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1, true>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+      else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+      else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
+      CKL(h, "decode_attn_kernel");
+      next_link(grid.x);
+    }
+    TRY(skinny(gemm_skinny(ctx, D * ks, l.wo.as<bf16>(), D * ks, R, D, D * ks, nullptr, ACT_NONE, t, D, false, kOutProjSplits, skip, pdl)));
     TRY(ln(ln_partials(t, kOutProjSplits, R, l.bo.as<float>(), xd, l.lnag.as<float>(), l.lnab.as<float>(), xd, hd)));
-    TRY(skinny(gemm_skinny(hd, D, l.w1.as<bf16>(), D, R, F, D, l.b1.as<float>(), ACT_GELU_ERF, u, F, true, 1, skip, pdl)));
-    TRY(skinny(gemm_skinny(u, F, l.w2.as<bf16>(), F, R, D, F, nullptr, ACT_NONE, t, D, false, kFc2Splits, skip, pdl)));
+    {
+      GemmCall c1 = gemm_skinny(hd, D * ks, l.w1.as<bf16>(), D * ks, R, F, D * ks, l.b1.as<float>(), ACT_GELU_ERF, u, static_cast<long long>(F) * ks, true, 1, skip, pdl);
+      c1.p.split3 = par ? 1 : 0;
+      TRY(skinny(c1));
+    }
+    TRY(skinny(gemm_skinny(u, F * ks, l.w2.as<bf16>(), F * ks, R, D, F * ks, nullptr, ACT_NONE, t, D, false, kFc2Splits, skip, pdl)));
     TRY(ln(ln_partials(t, kFc2Splits, R, l.b2.as<float>(), xd, l.lnog.as<float>(), l.lnob.as<float>(), xd, hd)));
   }
   if (lm_head)
-    TRY(skinny(gemm_skinny(hd, D, h->words_bf16.as<bf16>(), D, R, h->V, D, h->out_bias.as<float>(), ACT_NONE, logits, h->V, false, 1, skip, pdl)));
+    TRY(skinny(gemm_skinny(hd, D * ks, h->words_bf16.as<bf16>(), D * ks, R, h->V, D * ks, h->out_bias.as<float>(), ACT_NONE, logits, h->V, false, 1, skip, pdl)));
   ln_.chain_idx = cs.idx;
   ln_.chain_ctas = cs.pred_ctas;
   return 0;

@@ -265,7 +265,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-enum Act : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU_ERF = 2 };
+enum Act : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU_ERF = 2, ACT_QUICKGELU_EXACT = 3 };
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo == x to ~2^-17 relative: the operand format of the engine's fp32-grade parity
+// mode, where every GEMM runs as sum_k (a_hi w_hi + a_lo w_hi + a_hi w_lo) through the same tcgen05 kernel by laying the
+// three products side by side along K ("[hi | lo | hi]" activations against "[hi | hi | lo]" weights).
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ void pack_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 ah, al, bh, bl;
+  split_bf16(a, ah, al);
+  split_bf16(b, bh, bl);
+  hi = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
+  lo = static_cast<uint32_t>(__bfloat16_as_ushort(al)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl)) << 16);
+}
 
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -280,6 +295,8 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     // the ex2 + rcp form made the c_fc epilogue MUFU-bound (16 ops/clk/SM).
     const float hx = 0.5f * x;
     return fmaf(hx, tanh_approx(0.851f * x), hx);
+  } else if (act == ACT_QUICKGELU_EXACT) {   // parity mode: the sigmoid itself (expf, full-precision division)
+    return x / (1.0f + expf(-1.702f * x));
   } else if (act == ACT_GELU_ERF) {
     // reference layers/bert/activations.py:16-23: x * 0.5 * (1 + erf(x / sqrt(2))).
     // erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-exact for our purposes) with one ex2 and

@@ -36,6 +36,7 @@ struct LnParams {
   const float* temb;     // [F, D] or null
   int remap_B, remap_F, remap_L;  // remap_F == 0 -> identity
   const int* skip_flag;  // device int: non-zero -> kernel is a no-op (finished decode)
+  int split3;            // parity mode: out_bf16 rows are [hi | lo | hi] (3 x D columns, see split_bf16 in ptx.cuh)
   ChainSync chain;       // decode-step flag ordering (counters == null: plain / PDL ordering)
 };
 
@@ -146,7 +147,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
     }
     if (p.out_f32 != nullptr) reinterpret_cast<float4*>(p.out_f32 + orow * D)[i * 32 + lane] = o;
-    if (p.out_bf16 != nullptr) {
+    if (p.out_bf16 != nullptr && p.split3) {
+      uint2 hi, lo;
+      pack_split2(o.x, o.y, hi.x, lo.x);
+      pack_split2(o.z, o.w, hi.y, lo.y);
+      uint2* dst = reinterpret_cast<uint2*>(p.out_bf16 + orow * 3 * D) + i * 32 + lane;
+      dst[0] = hi; dst[D / 4] = lo; dst[D / 2] = hi;
+    } else if (p.out_bf16 != nullptr) {
       uint2 pk;
       pk.x = pack_bf16(o.x, o.y);
       pk.y = pack_bf16(o.z, o.w);
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
 // Patch im2col for the stride==kernel conv (reference layers/CLIP/model.py:224,242):
 // A[(img, py, px)][(c, ky, kx)] = img[c, py*p+ky, px*p+kx], zero-padded to Kp columns, bf16.
 __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int n_img, int H, int W,
-                                    int p, int gh, int gw, int Kp) {
+                                    int p, int gh, int gw, int Kp, int split3) {
   const long long total = static_cast<long long>(n_img) * gh * gw * (Kp / 8);
   const int K = 3 * p * p;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -183,6 +190,16 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __nv_bfloat16
         x = __ldg(img + ((im * 3 + c) * H + (py * p + ky)) * static_cast<long long>(W) + (px * p + kx));
       }
       v[j] = x;
+    }
+    if (split3) {   // parity mode: [hi | lo | hi], 3 x Kp columns
+      uint4 hi, lo;
+      pack_split2(v[0], v[1], hi.x, lo.x);
+      pack_split2(v[2], v[3], hi.y, lo.y);
+      pack_split2(v[4], v[5], hi.z, lo.z);
+      pack_split2(v[6], v[7], hi.w, lo.w);
+      uint4* dst = reinterpret_cast<uint4*>(A + row * 3 * Kp) + kc;
+      dst[0] = hi; dst[Kp / 8] = lo; dst[Kp / 4] = hi;
+      continue;
     }
     uint4 o;
     o.x = pack_bf16(v[0], v[1]);
@@ -292,7 +309,7 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const long long* __restrict__ tokens, long long tok_stride, const float* __restrict__ words,
                 const float* __restrict__ positions, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int rows, int pos_base,
-                const StepState* __restrict__ state, int vocab, const ChainSync chain) {
+                const StepState* __restrict__ state, int vocab, int split3, const ChainSync chain) {
   constexpr int NV = D / 128;
   griddep_launch();
   griddep_wait();   // chain head: ordered after the previous step by a full dependency
@@ -333,10 +350,18 @@ embed_ln_kernel(const long long* __restrict__ tokens, long long tok_stride, cons
     float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
                            (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
     reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * D)[i * 32 + lane] = o;
-    uint2 pk;
-    pk.x = pack_bf16(o.x, o.y);
-    pk.y = pack_bf16(o.z, o.w);
-    reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[i * 32 + lane] = pk;
+    if (split3) {
+      uint2 hi, lo;
+      pack_split2(o.x, o.y, hi.x, lo.x);
+      pack_split2(o.z, o.w, hi.y, lo.y);
+      uint2* dst = reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * 3 * D) + i * 32 + lane;
+      dst[0] = hi; dst[D / 4] = lo; dst[D / 2] = hi;
+    } else {
+      uint2 pk;
+      pk.x = pack_bf16(o.x, o.y);
+      pk.y = pack_bf16(o.z, o.w);
+      reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[i * 32 + lane] = pk;
+    }
   }
   chain_signal(chain);
 }

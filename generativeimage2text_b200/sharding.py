@@ -1,6 +1,6 @@
 """Image-wise data parallelism of the TSV path: one process per GPU, the rank's contiguous slice of the rows
-(identical to reference inference.py:152-169), and ONE collective at the end -- an all_gather of the finished
-token ids / logprobs -- replacing the reference's per-rank TSV part files + 5 s filesystem poll + byte concat
+(identical to reference inference.py:152-169), and ONE collective at the end -- a single all_gather of the finished
+token ids with the logprobs packed beside them -- replacing the reference's per-rank TSV part files + 5 s filesystem poll + byte concat
 (reference inference.py:159-164, 213-225).  Images are independent, so there is no collective on the data path.
 """
 import math
@@ -42,14 +42,14 @@ def gather_captions(tokens, logprobs, num_rows, pad_token=102, group=None):
     world = dist.get_world_size(group)
     per = int(math.ceil(num_rows / world))
     T = tokens.shape[1]
-    # int32 on the wire (vocabulary ids < 2^31): [per, T] int32 + [per] fp32 per rank
-    buf_t = torch.full((per, T), pad_token, dtype=torch.int32, device=tokens.device)
-    buf_l = torch.zeros((per,), dtype=torch.float32, device=tokens.device)
+    # ONE collective: int32 on the wire (vocabulary ids < 2^31), [per, T + 1] per rank -- the last column carries the fp32
+    # logprob's bit pattern
+    buf = torch.full((per, T + 1), pad_token, dtype=torch.int32, device=tokens.device)
     n = tokens.shape[0]
-    buf_t[:n] = tokens.to(torch.int32)
-    buf_l[:n] = logprobs.reshape(-1)[:n]
-    all_t = torch.empty((world * per, T), dtype=torch.int32, device=tokens.device)
-    all_l = torch.empty((world * per,), dtype=torch.float32, device=tokens.device)
-    dist.all_gather_into_tensor(all_t, buf_t, group=group)
-    dist.all_gather_into_tensor(all_l, buf_l, group=group)
-    return all_t[:num_rows].long(), all_l[:num_rows]
+    buf[:n, :T] = tokens.to(torch.int32)
+    lp = torch.zeros((per,), dtype=torch.float32, device=tokens.device)
+    lp[:n] = logprobs.reshape(-1)[:n].float()
+    buf[:, T] = lp.view(torch.int32)
+    out = torch.empty((world * per, T + 1), dtype=torch.int32, device=tokens.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return out[:num_rows, :T].long(), out[:num_rows, T].contiguous().view(torch.float32)

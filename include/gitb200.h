@@ -144,7 +144,10 @@ int gitb200_generate_finish(gitb200_engine* h, int32_t* out_len_host);
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t gitb200_launch_count(const gitb200_engine* h);
 /* Engine switches (defaults in parentheses): use_graph (1) CUDA-graph replay of the decode step, use_pdl (1) programmatic
- * dependent launch inside the step, use_chain (1) flag-ordered decode chain, use_2cta (1) cta_group::2 encoder GEMMs. */
+ * dependent launch inside the step, use_chain (1) flag-ordered decode chain, use_2cta (1) cta_group::2 encoder GEMMs,
+ * parity (0) fp32-grade verification mode: every GEMM operand is a (hi, lo) bf16 pair and each product is computed as
+ * a_hi w_hi + a_lo w_hi + a_hi w_lo by the same tcgen05 kernel (three K-segments side by side), attention / K/V caches /
+ * q, k, v in fp32 -- set it BEFORE gitb200_set_weight (switching it forgets the uploaded weights). */
 int gitb200_set_option(gitb200_engine* h, const char* name, int64_t value);
 
 /* ---- single-kernel entry points (unit tests, micro-benchmarks, ncu) -------------------------------- */

@@ -523,3 +523,100 @@ def test_long_max_steps_grows_the_text_cache():
     torch.cuda.synchronize()
     assert out['predictions'].shape == (3, 1024)
     assert m.launch_count() - before < 400 * 48, 'the beam loop enqueued (almost) all 1023 steps'
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp32-grade parity mode (engine option 'parity'): the north star's "logits within 1e-3", token-identical greedy output
+# ------------------------------------------------------------------------------------------------------------------
+PARITY_ATOL = 1e-3
+
+
+def _parity_model(meta, sd, **kw):
+    m = _model(meta, sd, **kw)
+    m.set_engine_option('parity', 1)
+    return m
+
+
+@pytest.mark.parametrize('name', ['base_greedy_init', 'base_greedy', 'base_prefix', 'vatex_greedy', 'large_greedy',
+                                  'base_ratio_greedy', 'base_decisive'])
+def test_parity_mode_logits_within_1e3_of_the_fp32_reference(name):
+    """Every GEMM as a three-term (hi, lo) bf16 split product through the same tcgen05 kernels, fp32 attention and caches:
+    image features, visual projection and every step's full logit row within 1e-3 of the fp32 oracle (and of the
+    reference's own numbers at the golden's sampled columns), teacher-forced; decisions equal wherever the margin exceeds
+    2.5x the measured error; and the FREE-RUNNING captions equal the reference's whenever every margin along the way does."""
+    g = load_golden(name)
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    P = len(meta.get('prefix', [101]))
+    raw = []
+    ref = git_oracle.generate(sd, meta['param'], batch, 'greedy', meta['max_steps'], cached=True, raw_trace=raw)
+    ref_pred = ref['predictions']
+    full_ref = torch.cat([batch['prefix'].long(), ref_pred], dim=1) if 'prefix' in batch else ref_pred
+    m = _parity_model(meta, sd)
+    feats = m.encode_image(_to_cuda(batch)['image'])
+    vproj = m.prefill(meta['batch'])
+    torch.cuda.synchronize()
+    rf = git_oracle.visual_features(sd, meta['param'], batch['image'])
+    e_f = (feats.cpu() - rf).abs().max().item()
+    e_p = (vproj.cpu() - git_oracle.project_visual(sd, rf)).abs().max().item()
+    forced = torch.full((meta['batch'], meta['max_steps']), 102, dtype=torch.long)
+    forced[:, :full_ref.shape[1]] = full_ref
+    out = m(_to_cuda(batch), forced_tokens=forced, return_step_logits=True)
+    torch.cuda.synchronize()
+    z = out['step_logits'].cpu()
+    own = out['predictions'].cpu()
+    cols = torch.from_numpy(g['vocab_cols'])
+    worst = max((z[i] - r).abs().max().item() for i, r in enumerate(raw))
+    print('%s [parity]: features max err %.2e, vproj %.2e, logits %.2e (north star: 1e-3)' % (name, e_f, e_p, worst))
+    assert e_f < PARITY_ATOL and e_p < PARITY_ATOL and worst < PARITY_ATOL
+    min_margin = float('inf')
+    for i, r in enumerate(raw):
+        np.testing.assert_allclose(z[i][:, cols].numpy(), g['step_logits'][i], rtol=0, atol=PARITY_ATOL + 5e-4)
+        tok_in = None if i == 0 else full_ref[:, P + i - 1]
+        margin = greedy_margins(r, tok_in)
+        col = (0 if 'prefix' in batch else P) + i
+        for b in range(meta['batch']):
+            if tok_in is not None and tok_in[b].item() == 102:
+                continue                                     # the row has ended: EOS is forced
+            min_margin = min(min_margin, margin[b].item())
+            if margin[b].item() > 2.5 * worst:
+                assert own[b, col].item() == ref_pred[b, col].item(), (name, i, b, margin[b].item())
+    free = m(_to_cuda(batch))
+    torch.cuda.synchronize()
+    same = free['predictions'].shape == ref_pred.shape and bool((free['predictions'].cpu() == ref_pred).all())
+    print('%s [parity]: smallest reference margin %.2e; free-running captions token-identical: %s' % (name, min_margin, same))
+    if min_margin > 4 * worst:
+        assert same
+        np.testing.assert_allclose(free['logprobs'].cpu().numpy().reshape(-1), g['logprobs'].reshape(-1), rtol=0, atol=2e-3)
+
+
+def test_parity_mode_beam_trajectory():
+    """Beam search rows (4 beams per image sharing the fp32 image K/V, text K/V re-ordered by beam_idx) in parity mode."""
+    g = load_golden('base_beam')
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    m = _parity_model(meta, sd)
+    B = meta['batch']
+    m.encode_image(_to_cuda(batch)['image'])
+    m.prefill(B, beam=4)
+    feats = git_oracle.visual_features(sd, meta['param'], batch['image'])
+    dec = git_oracle.CachedDecoder(sd, feats, beam=4)
+    pending = {'idx': None}
+    worst = [0.0]
+
+    def step(ids):
+        pos = dec.n_text
+        ref = dec.feed(ids[:, pos:])
+        mine = m.decoding_step(ids[:, -1], pos, beam_idx=pending['idx']).cpu()
+        pending['idx'] = None
+        worst[0] = max(worst[0], (mine - ref).abs().max().item())
+        return ref
+
+    def reorder(bidx):
+        dec.reorder(bidx)
+        pending['idx'] = bidx
+
+    pred, lp = git_oracle.beam_search(torch.full((B, 1), 101, dtype=torch.long), step, reorder=reorder, max_steps=meta['max_steps'])
+    assert np.array_equal(pred.numpy(), g['predictions'])
+    print('base_beam [parity]: beam trajectory max |logit - oracle| %.2e' % worst[0])
+    assert worst[0] < PARITY_ATOL

@@ -8,7 +8,9 @@ import git_oracle
 from helpers import load_golden, golden_inputs
 
 CASES = ['base_greedy_init', 'base_greedy', 'base_beam', 'base_prefix', 'vatex_greedy',
-         'large_greedy', 'large_beam', 'base_ratio_greedy', 'base_crop160_greedy', 'base_vqa_ratio_greedy']
+         'large_greedy', 'large_beam', 'base_ratio_greedy', 'base_crop160_greedy', 'base_vqa_ratio_greedy',
+         # round 2: the benchmarked configurations at their benchmarked batch sizes, and the decisive-margin checkpoint
+         'base_greedy_b64', 'vatex_greedy_b16', 'large_beam_b32', 'base_decisive']
 
 
 @pytest.mark.parametrize('name', CASES)
