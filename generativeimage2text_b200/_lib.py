@@ -65,6 +65,7 @@ SIGNATURES = {
                                     ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_int64, c_void_p]),
     'gitb200_preproc_coeffs': (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_void_p, c_void_p, c_int]),
     'gitb200_debug_timeline': (c_int, [c_int, c_void_p, c_int]),
+    'gitb200_debug_read': (c_ll, [c_void_p, c_char_p, c_void_p, c_ll]),
     'gitb200_op_gemm': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
     'gitb200_op_layernorm': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgitb200.so')
 SOURCES = ['gitb200.cu']
-DEPS = ['gitb200.cu', 'engine_api.inc', 'ptx.cuh', 'gemm.cuh', 'gemm2.cuh', 'rowops.cuh', 'attention.cuh',
+DEPS = ['gitb200.cu', 'engine_api.inc', 'ptx.cuh', 'gemm.cuh', 'gemm2.cuh', 'rowops.cuh', 'attention.cuh', 'decode_mega.cuh',
         'search.cuh', 'preproc.cuh', 'preproc_api.inc',
         os.path.join('..', '..', 'include', 'gitb200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -36,7 +36,10 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu -> libgitb200.so (no-op when up to date). Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB]
+    flags = list(NVCC_FLAGS)
+    if os.environ.get('GITB200_TIMELINE'):      # debug build with the in-situ decode-step timeline (tools/step_timeline2.py)
+        flags.append('-DGITB200_TIMELINE')
+    cmd = [_nvcc()] + flags + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     r = subprocess.run(cmd, capture_output=True, text=True)

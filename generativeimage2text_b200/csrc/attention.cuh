@@ -180,6 +180,214 @@ __global__ void __launch_bounds__(NW * 32) flash_attn_kernel(const AttnParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// flash_attn_tc_kernel: the same non-causal attention on the 5th-generation tensor cores, for sequences that fit the
+// tensor memory in one piece (S <= 512 keys: the ViT blocks and the image-row prefill of the image models).
+//   One CTA per (batch, head).  K and V of the head are fetched ONCE by TMA (128B-swizzled boxes) and stay in shared
+//   memory; per 128-row query tile:  TMA Q -> tcgen05.mma S = Q K^T (fp32, TMEM columns [0, Spad)) -> the four softmax
+//   warps read their TMEM lane (= query row, so row max / row sum need no shuffles), write P = exp2(...) as bf16 into
+//   shared memory in the K-major swizzled operand layout -> tcgen05.mma O = P V with V as an MN-major B operand (V stays
+//   [key][dim] as TMA delivered it), O overwriting TMEM columns [0, 64) -> the softmax warps scale by 1 / row sum and
+//   store bf16 rows.
+//   Warp 0: TMA + MMA issue (one lane); warps 1-4: softmax / epilogue (TMEM lane quadrants 1, 2, 3, 0).
+// ------------------------------------------------------------------------------------------------
+struct AttnTcParams {
+  __nv_bfloat16* out;
+  int B, S, H;
+  int spad;                 // keys padded to a multiple of 16 (MMA N / K granularity)
+  int kv_box_rows, kv_boxes;   // K / V arrive as kv_boxes TMA boxes of kv_box_rows rows (kv_box_rows * kv_boxes >= spad)
+  long long q_rows_per_batch, kv_rows_per_batch;   // row coordinate of batch b in the tensor maps = b * rows_per_batch
+  int q_col0, k_col0, v_col0;                      // column of head 0 inside the tensor maps (heads are 64 columns apart)
+  long long o_rs, o_bs;
+  float scale_log2;
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+constexpr int kAttnTcThreads = 160;
+__host__ __device__ inline size_t attn_tc_smem_bytes(int spad, int kv_box_rows, int kv_boxes) {
+  const size_t kv = static_cast<size_t>(kv_box_rows) * kv_boxes * 128;
+  const size_t pblk = static_cast<size_t>((spad + 63) / 64) * 16384;
+  return 1024 + 2 * ((kv + 1023) / 1024 * 1024) + pblk + 128;
+}
+
+// bounded wait: a protocol bug must show up as wrong numbers in a test, never as a hung device
+__device__ __forceinline__ void mbar_wait_lim(uint64_t* bar, uint32_t parity) {
+  for (unsigned int i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+}
+
+__global__ void __launch_bounds__(kAttnTcThreads, 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t attn_tc_raw[];
+  uint8_t* smem = attn_tc_raw + ((1024u - (smem_u32(attn_tc_raw) & 1023u)) & 1023u);
+  const size_t kv_bytes = (static_cast<size_t>(p.kv_box_rows) * p.kv_boxes * 128 + 1023) / 1024 * 1024;
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kv_bytes;
+  uint8_t* sP = smem + 2 * kv_bytes;                 // k-blocks of [128 rows x 64 keys]; block 0 doubles as the Q tile
+  const int n_pblk = (p.spad + 63) / 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + static_cast<size_t>(n_pblk) * 16384);
+  uint64_t* bar_kv = bars;       // K and V landed
+  uint64_t* bar_q = bars + 1;    // Q tile landed
+  uint64_t* bar_s = bars + 2;    // S complete in TMEM
+  uint64_t* bar_p = bars + 3;    // P written (4 warps)
+  uint64_t* bar_o = bars + 4;    // O complete in TMEM
+  uint64_t* bar_free = bars + 5; // the softmax warps are done with O (4 warps): TMEM and the Q / P region may be reused
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int n_tiles = (p.S + 127) / 128;
+  const uint32_t tmem_cols = (p.spad <= 256) ? 256u : 512u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_free, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // K and V of this (batch, head): once
+      mbar_arrive_expect_tx(bar_kv, static_cast<uint32_t>(2 * p.kv_boxes * p.kv_box_rows * 128));
+      for (int i = 0; i < p.kv_boxes; ++i) {
+        const int row = static_cast<int>(b * p.kv_rows_per_batch) + i * p.kv_box_rows;
+        tma_load_2d(sK + static_cast<size_t>(i) * p.kv_box_rows * 128, &tmK, bar_kv, p.k_col0 + h * 64, row);
+        tma_load_2d(sV + static_cast<size_t>(i) * p.kv_box_rows * 128, &tmV, bar_kv, p.v_col0 + h * 64, row);
+      }
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);     // B operand (V) is MN-major
+      for (int tile = 0; tile < n_tiles; ++tile) {
+        const uint32_t ph = tile & 1;
+        if (tile > 0) { mbar_wait_lim(bar_free, ph ^ 1); tc_fence_after(); }
+        mbar_arrive_expect_tx(bar_q, 128 * 128);
+        tma_load_2d(sP, &tmQ, bar_q, p.q_col0 + h * 64, static_cast<int>(b * p.q_rows_per_batch) + tile * 128);
+        if (tile == 0) mbar_wait_lim(bar_kv, 0);
+        mbar_wait_lim(bar_q, ph);
+        tc_fence_after();
+        // S = Q K^T: N in pieces of <= 256 key columns, K = 64 head dims = 4 MMAs each
+        for (int n0 = 0; n0 < p.spad; n0 += 256) {
+          const int nn = min(256, p.spad - n0);
+          const uint32_t idesc = umma_idesc_bf16(128, nn);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + n0, umma_desc_sw128(smem_u32(sP) + k * 32), umma_desc_sw128(smem_u32(sK) + n0 * 128 + k * 32), idesc,
+                      k > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_s);
+        // O = P V once the softmax warps have written P
+        mbar_wait_lim(bar_p, ph);
+        tc_fence_after();
+        const int nk16 = p.spad / 16;
+        for (int kb = 0; kb < nk16; ++kb)
+          umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sP) + (kb >> 2) * 16384 + (kb & 3) * 32),
+                    umma_desc_sw128(smem_u32(sV) + kb * 2048), idesc_pv, kb > 0 ? 1u : 0u);
+        umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ---- softmax / epilogue: thread = query row = TMEM lane ----
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                 // row of the tile
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int n16 = p.spad / 16;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const uint32_t ph = tile & 1;
+      mbar_wait_lim(bar_s, ph);
+      tc_fence_after();
+      float mx = -INFINITY;
+      for (int c = 0; c < n16; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_lane + c * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c * 16 + j < p.S) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
+      float sum = 0.f;
+      const float mb = mx * p.scale_log2;
+      for (int c = 0; c < n16; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_lane + c * 16, r);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float p0 = (c * 16 + 2 * j < p.S) ? exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mb)) : 0.f;
+          const float p1 = (c * 16 + 2 * j + 1 < p.S) ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mb)) : 0.f;
+          sum += p0 + p1;
+          pk[j] = pack_bf16(p0, p1);
+        }
+        uint8_t* blk = sP + (c >> 2) * 16384 + row * 128;
+        const int ch = 2 * (c & 3);
+        *reinterpret_cast<uint4*>(blk + (((ch) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(blk + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      // ---- O / row sum -> bf16 row ----
+      mbar_wait_lim(bar_o, ph);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      const int qrow = tile * 128 + row;
+      __nv_bfloat16* orow = p.out + b * p.o_bs + static_cast<long long>(qrow) * p.o_rs + h * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_lane + c * 16, r);
+        tmem_ld_wait();
+        if (qrow < p.S) {
+          uint4 v0, v1;
+          v0.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+          v0.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+          v0.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+          v0.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+          v1.x = pack_bf16(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+          v1.y = pack_bf16(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+          v1.z = pack_bf16(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+          v1.w = pack_bf16(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+          reinterpret_cast<uint4*>(orow + c * 16)[0] = v0;
+          reinterpret_cast<uint4*>(orow + c * 16)[1] = v1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct DecAttnParams {
   const float* qkv;                // [n_partials][R, 3*D] fp32 (q | k | v): the QKV GEMM's split-K partial sums, added
   int n_partials;                  //   here in split order (1..4 buffers, partial_stride elements apart)

@@ -54,7 +54,8 @@ struct MegaParams {
   int R, M, T_alloc, V, n_layers;
   // activations (global, L2 resident)
   float* x;                // [R, 768] residual stream (post-LayerNorm)
-  float* y;                // [R, 768] pre-LayerNorm sum
+  float* y;                // [R, 768] pre-LayerNorm sum (after the attention block)
+  float* ypart;            // [4][R, 768] fc2 partial sums of the four 768-wide k slices (summed in slice order by the LN)
   __nv_bfloat16* hb;       // [R, 768] bf16 copy of x (GEMM operand)
   __nv_bfloat16* qb;       // [R, 768] q (+bias) / 8
   __nv_bfloat16* ctx;      // [R, 768]
@@ -128,11 +129,14 @@ __device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned i
   named_bar_sync(1, kMegaComputeWarps * 32);
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
+    tl_mark_one(500000 + static_cast<int>(epoch / gridDim.x));      // this CTA arrived at barrier #n
+    __threadfence();
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
     unsigned int spins = 0;
     while (ld_acquire_gpu(counter) < epoch) {
       if (++spins > kMegaSpinLimit) { *error = 1; break; }
     }
+    tl_mark_one(600000 + static_cast<int>(epoch / gridDim.x));      // barrier #n released
   }
   named_bar_sync(1, kMegaComputeWarps * 32);
 }
@@ -153,9 +157,13 @@ __device__ __forceinline__ void mega_load_a(MegaAFrag& a, const __nv_bfloat16* A
     a.hi[j] = (r1 < rows) ? __ldcg(p1 + 4 * j) : make_uint4(0, 0, 0, 0);
   }
 }
-// c += A(16 x 384 of this warp) * tile(8 features, this warp's k half)
+// c += A(16 x 384 of this warp) * tile(8 features, this warp's k half).  Two independent accumulators (even / odd k-steps):
+// a single one would serialise 24 dependent MMAs (~0.4 us per tile, which made the 26-tile LM head latency bound); they
+// are added in a fixed order, so the result stays bit-reproducible.  (Four would spill: 9 warps cap the kernel at 168
+// registers per thread.)
 __device__ __forceinline__ void mega_mma_tile(float (&c)[4], const MegaAFrag& a, const uint8_t* tile, int kh, int lane) {
   const uint2* bp = reinterpret_cast<const uint2*>(tile) + kh * 24 * 32 + lane;
+  float c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
     const uint2 b0 = bp[(2 * j) * 32];
@@ -163,8 +171,10 @@ __device__ __forceinline__ void mega_mma_tile(float (&c)[4], const MegaAFrag& a,
     const uint32_t a0[4] = {a.lo[j].x, a.hi[j].x, a.lo[j].y, a.hi[j].y};
     const uint32_t a1[4] = {a.lo[j].z, a.hi[j].z, a.lo[j].w, a.hi[j].w};
     mma_bf16_16816(c, a0, b0.x, b0.y);
-    mma_bf16_16816(c, a1, b1.x, b1.y);
+    mma_bf16_16816(c1, a1, b1.x, b1.y);
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) c[e] += c1[e];
 }
 
 // Sum of the two K halves: the kh = 1 warp parks its accumulator in shared memory, its kh = 0 partner adds it.
@@ -254,7 +264,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
         }
         if (cta < 96) tile(L.wo + static_cast<size_t>(cta) * kMegaTileBytes);
         if (cta < 128) for (int j = 0; j < 3; ++j) tile(L.w1 + static_cast<size_t>(cta * 3 + j) * kMegaTileBytes);
-        if (cta < 96) for (int s = 0; s < 4; ++s) tile(L.w2 + static_cast<size_t>(cta * 4 + s) * kMegaTileBytes);
+        if (cta < 96) for (int j = 0; j < 4; ++j) tile(L.w2 + static_cast<size_t>(((cta >> 2) * 4 + j) * 4 + (cta & 3)) * kMegaTileBytes);
       }
       for (int j = 0; j < lm_n; ++j) tile(p.lm + static_cast<size_t>(lm_t0 + j) * kMegaTileBytes);
     }
@@ -276,6 +286,10 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
     if (cta < 144) {
       MegaAFrag a;
       mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
+      float2 bias_j[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bias_j[j] = __ldg(reinterpret_cast<const float2*>(L.bqkv + (cta * 2 + j) * 8 + 2 * t));
+#pragma unroll
       for (int j = 0; j < 2; ++j) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
         const uint8_t* tb = rg.acquire();
@@ -283,7 +297,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
         rg.release();
         if (mega_combine(c, red, red_buf, mt, kh, lane)) {
           const int f = (cta * 2 + j) * 8 + 2 * t;
-          const float2 bias = *reinterpret_cast<const float2*>(L.bqkv + f);
+          const float2 bias = bias_j[j];
           const int seg = f / kMegaD, fo = f - seg * kMegaD;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -303,15 +317,39 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
     }
     mega_grid_sync(bar, epoch, p.error);
     // ------------------------------------------------ P2: attention ------------------------------------------------
+    // What an item needs from L2 (its query row, the text K/V rows of the caption so far) is requested one item ahead:
+    // a CTA walks 5-6 items per layer and an exposed L2 round trip per item would cost more than the item's HBM stream.
+    constexpr int kTxtPre = 5;                      // text positions per warp held in registers (8 warps x 5 = 40 positions)
+    struct AttPre { uint4 q; uint32_t kr[kTxtPre], vr[kTxtPre]; };
+    auto att_prefetch = [&](int k, AttPre& pr) {
+      pr.q = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < kTxtPre; ++i) { pr.kr[i] = 0u; pr.vr[i] = 0u; }
+      if (k < n_my_items) {
+        const int item = my_cta_rev + k * G;
+        const int b = item / kMegaH, h = item - b * kMegaH;
+        if (tid < 8) pr.q = __ldcg(reinterpret_cast<const uint4*>(p.qb + static_cast<long long>(b) * kMegaD + h * 64) + tid);
+#pragma unroll
+        for (int i = 0; i < kTxtPre; ++i) {
+          const int j = warp + kMegaComputeWarps * i;
+          if (j <= pos) {
+            const long long off = (static_cast<long long>(b) * p.T_alloc + j) * kMegaD + h * 64 + 2 * lane;
+            pr.kr[i] = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_k + off));
+            pr.vr[i] = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_v + off));
+          }
+        }
+      }
+    };
+    AttPre cur, nxt;
+    att_prefetch(0, cur);
     for (int k = 0; k < n_my_items; ++k) {
       const int item = my_cta_rev + k * G;
       const int b = item / kMegaH, h = item - b * kMegaH;
+      att_prefetch(k + 1, nxt);
       // q tile: row 0 = this sequence's query (already scaled by 1/8), rows 1..15 zero; 128B-swizzled like the K/V boxes
       if (tid < 128) {
         const int row = tid >> 3, ch = tid & 7;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row == 0) v = __ldcg(reinterpret_cast<const uint4*>(p.qb + static_cast<long long>(b) * kMegaD + h * 64) + ch);
-        *reinterpret_cast<uint4*>(q_s + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+        *reinterpret_cast<uint4*>(q_s + row * 128 + ((ch ^ (row & 7)) << 4)) = (row == 0) ? cur.q : make_uint4(0, 0, 0, 0);
       }
       named_bar_sync(1, kMegaComputeWarps * 32);
       uint32_t qa[4][4];
@@ -394,10 +432,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
       {
         const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(q_s + ((lane >> 2) << 4) + ((lane & 3) << 2));  // row 0: chunk ^ 0
         const float qx = __bfloat162float(q2.x), qy = __bfloat162float(q2.y);
-        for (int j = warp; j <= pos; j += kMegaComputeWarps) {
-          const long long off = (static_cast<long long>(b) * p.T_alloc + j) * kMegaD + h * 64 + 2 * lane;
-          const uint32_t kr = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_k + off));
-          const uint32_t vr = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_v + off));
+        auto text_key = [&](uint32_t kr, uint32_t vr) {
           const float sc = warp_sum(qx * bf16_lo(kr) + qy * bf16_hi(kr));
           const float mn = fmaxf(tm, sc);
           const float cr = exp2f((tm - mn) * kLog2e);
@@ -406,6 +441,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
           to0 = to0 * cr + pe * bf16_lo(vr);
           to1 = to1 * cr + pe * bf16_hi(vr);
           tm = mn;
+        };
+#pragma unroll
+        for (int i = 0; i < kTxtPre; ++i)
+          if (warp + kMegaComputeWarps * i <= pos) text_key(cur.kr[i], cur.vr[i]);       // warp-uniform predicate
+        for (int j = warp + kMegaComputeWarps * kTxtPre; j <= pos; j += kMegaComputeWarps) {   // captions longer than 40 tokens
+          const long long off = (static_cast<long long>(b) * p.T_alloc + j) * kMegaD + h * 64 + 2 * lane;
+          text_key(__ldcg(reinterpret_cast<const unsigned int*>(L.txt_k + off)), __ldcg(reinterpret_cast<const unsigned int*>(L.txt_v + off)));
         }
       }
       // ---- merge the 16 partial softmax states (8 image-key partials, 8 text-key partials) ----
@@ -437,39 +479,64 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
         p.ctx[static_cast<long long>(b) * kMegaD + h * 64 + tid] = __float2bfloat16_rn(acc / lsum);
       }
       named_bar_sync(1, kMegaComputeWarps * 32);      // q_s / att_part are rewritten by the next item
+      cur = nxt;
     }
     mega_grid_sync(bar, epoch, p.error);
     // ------------------------------------------------ P3: attention output projection (+bias +residual) ------------------
     if (cta < 96) {
       MegaAFrag a;
       mega_load_a(a, p.ctx, kMegaD, R, mt, kh, lane);
+      const int f = cta * 8 + 2 * t;
+      const float2 bias = __ldg(reinterpret_cast<const float2*>(L.bo + f));
+      float2 xr[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};      // residual: requested before the MMA needs the tile
+      if (kh == 0 && r0 < R) xr[0] = ldcg_f2(p.x + static_cast<long long>(r0) * kMegaD + f);
+      if (kh == 0 && r1 < R) xr[1] = ldcg_f2(p.x + static_cast<long long>(r1) * kMegaD + f);
       float c[4] = {0.f, 0.f, 0.f, 0.f};
       const uint8_t* tb = rg.acquire();
       mega_mma_tile(c, a, tb, kh, lane);
       rg.release();
       if (mega_combine(c, red, red_buf, mt, kh, lane)) {
-        const int f = cta * 8 + 2 * t;
-        const float2 bias = *reinterpret_cast<const float2*>(L.bo + f);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int r = hh ? r1 : r0;
           if (r >= R) continue;
-          const float2 xr = ldcg_f2(p.x + static_cast<long long>(r) * kMegaD + f);
           *reinterpret_cast<float2*>(p.y + static_cast<long long>(r) * kMegaD + f) =
-              make_float2(xr.x + (c[2 * hh] + bias.x), xr.y + (c[2 * hh + 1] + bias.y));
+              make_float2(xr[hh].x + (c[2 * hh] + bias.x), xr[hh].y + (c[2 * hh + 1] + bias.y));
         }
       }
       red_buf ^= 1;
     }
     mega_grid_sync(bar, epoch, p.error);
     // ------------------------------------------------ P4 / P7: LayerNorm(y) -> x, hb (one warp per row) -------------------
-    auto layer_norm_rows = [&](const float* gamma, const float* beta) {
+    // from_parts: the input row is x + ((p0 + p1) + p2) + p3 + bias (fc2's four k-slice partials, fixed order)
+    auto layer_norm_rows = [&](const float* gamma, const float* beta, bool from_parts, const float* bias) {
       const int row = cta * kMegaComputeWarps + warp;
       if (row < R) {
         float4 v[6];
-        const float4* yp = reinterpret_cast<const float4*>(p.y + static_cast<long long>(row) * kMegaD);
+        if (!from_parts) {
+          const float4* yp = reinterpret_cast<const float4*>(p.y + static_cast<long long>(row) * kMegaD);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) v[i] = __ldcg(yp + i * 32 + lane);
+          for (int i = 0; i < 6; ++i) v[i] = __ldcg(yp + i * 32 + lane);
+        } else {
+          const long long ps = static_cast<long long>(R) * kMegaD / 4;     // float4s per partial buffer
+          const float4* pp = reinterpret_cast<const float4*>(p.ypart + static_cast<long long>(row) * kMegaD);
+          const float4* xp = reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * kMegaD);
+          float4 q0[6], q1[6], q2[6], q3[6], xx[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            q0[i] = __ldcg(pp + i * 32 + lane); q1[i] = __ldcg(pp + ps + i * 32 + lane);
+            q2[i] = __ldcg(pp + 2 * ps + i * 32 + lane); q3[i] = __ldcg(pp + 3 * ps + i * 32 + lane);
+            xx[i] = __ldcg(xp + i * 32 + lane);
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + i * 32 + lane);
+            v[i].x = xx[i].x + ((((q0[i].x + q1[i].x) + q2[i].x) + q3[i].x) + bb.x);
+            v[i].y = xx[i].y + ((((q0[i].y + q1[i].y) + q2[i].y) + q3[i].y) + bb.y);
+            v[i].z = xx[i].z + ((((q0[i].z + q1[i].z) + q2[i].z) + q3[i].z) + bb.z);
+            v[i].w = xx[i].w + ((((q0[i].w + q1[i].w) + q2[i].w) + q3[i].w) + bb.w);
+          }
+        }
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -498,12 +565,16 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
         }
       }
     };
-    layer_norm_rows(L.lnag, L.lnab);
+    layer_norm_rows(L.lnag, L.lnab, false, nullptr);
     mega_grid_sync(bar, epoch, p.error);
     // ------------------------------------------------ P5: fc1 + erf-GELU ------------------------------------------------
     if (cta < 128) {
       MegaAFrag a;
       mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
+      float2 bias_j[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) bias_j[j] = __ldg(reinterpret_cast<const float2*>(L.b1 + (cta * 3 + j) * 8 + 2 * t));
+#pragma unroll
       for (int j = 0; j < 3; ++j) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
         const uint8_t* tb = rg.acquire();
@@ -511,7 +582,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
         rg.release();
         if (mega_combine(c, red, red_buf, mt, kh, lane)) {
           const int f = (cta * 3 + j) * 8 + 2 * t;
-          const float2 bias = *reinterpret_cast<const float2*>(L.b1 + f);
+          const float2 bias = bias_j[j];
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int r = hh ? r1 : r0;
@@ -524,32 +595,30 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
       }
     }
     mega_grid_sync(bar, epoch, p.error);
-    // ------------------------------------------------ P6: fc2 (+bias +residual), full K = 3072 in four slices ------------
+    // ------------------------------------------------ P6: fc2, split over CTAs: 24 groups of 32 features x 4 k slices ------
+    // (each CTA reads ONE 768-wide slice of the activations; the four partial sums of a feature meet, in slice order, in
+    //  the LayerNorm phase below -- bit-reproducible, no atomics)
     if (cta < 96) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int sl = 0; sl < 4; ++sl) {
-        MegaAFrag a;
-        mega_load_a(a, p.ub + sl * kMegaD, kMegaF, R, mt, kh, lane);
+      const int ks = cta & 3, fg = cta >> 2;
+      MegaAFrag a;
+      mega_load_a(a, p.ub + ks * kMegaD, kMegaF, R, mt, kh, lane);
+      float* yp = p.ypart + static_cast<long long>(ks) * R * kMegaD;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
         const uint8_t* tb = rg.acquire();
         mega_mma_tile(c, a, tb, kh, lane);
         rg.release();
-      }
-      if (mega_combine(c, red, red_buf, mt, kh, lane)) {
-        const int f = cta * 8 + 2 * t;
-        const float2 bias = *reinterpret_cast<const float2*>(L.b2 + f);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int r = hh ? r1 : r0;
-          if (r >= R) continue;
-          const float2 xr = ldcg_f2(p.x + static_cast<long long>(r) * kMegaD + f);
-          *reinterpret_cast<float2*>(p.y + static_cast<long long>(r) * kMegaD + f) =
-              make_float2(xr.x + (c[2 * hh] + bias.x), xr.y + (c[2 * hh + 1] + bias.y));
+        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+          const int f = (fg * 4 + j) * 8 + 2 * t;
+          if (r0 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r0) * kMegaD + f) = make_float2(c[0], c[1]);
+          if (r1 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r1) * kMegaD + f) = make_float2(c[2], c[3]);
         }
+        red_buf ^= 1;
       }
-      red_buf ^= 1;
     }
     mega_grid_sync(bar, epoch, p.error);
-    layer_norm_rows(L.lnog, L.lnob);
+    layer_norm_rows(L.lnog, L.lnob, true, L.b2);
     mega_grid_sync(bar, epoch, p.error);
   }
 
@@ -563,6 +632,12 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
     if (r1 < R) last1 = p.next_token[r1];
     float smax[2] = {-INFINITY, -INFINITY}, ssum[2] = {0.f, 0.f};
     int sarg[2] = {0x7fffffff, 0x7fffffff};
+    float* bias_s = att_part;                       // this CTA's slice of the output bias (<= 8 * lm_per floats)
+    for (int i = tid; i < lm_n * 8; i += kMegaComputeWarps * 32) {
+      const int col = lm_t0 * 8 + i;
+      bias_s[i] = (col < p.V) ? __ldg(p.lm_bias + col) : 0.f;
+    }
+    named_bar_sync(1, kMegaComputeWarps * 32);
     if (lm_n > 0) {
       MegaAFrag a;
       mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
@@ -582,7 +657,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
             for (int e = 0; e < 2; ++e) {
               const int col = f + e;
               if (col >= p.V) continue;
-              float v = c[2 * hh + e] + __ldg(p.lm_bias + col);
+              float v = c[2 * hh + e] + bias_s[j * 8 + 2 * t + e];
               if (p.step_logits != nullptr) p.step_logits[(static_cast<long long>(step) * R + r) * p.V + col] = v;
               if (!first && col == static_cast<int>(last)) v = -10000.0f;        // no-repeat (reference :330)
               if (v > smax[hh]) {            // columns arrive in increasing order: the lowest index wins exact ties

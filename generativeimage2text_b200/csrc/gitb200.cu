@@ -115,9 +115,11 @@ struct gitb200_engine {
   // a_hi w_lo in ONE pass of the same tcgen05 kernel (activations stored [hi | lo | hi], weights [hi | hi | lo] along K);
   // attention, K/V caches and q/k/v stay fp32; exact QuickGELU.  ~3x the GEMM work: a verification mode (the north star's
   // "logits within 1e-3" against the fp32 reference), not a serving mode.  Weights must be (re-)uploaded after switching.
+  bool tc_attn = true;    // ViT / prefill attention on tcgen05 (flash_attn_tc_kernel) when the sequence fits TMEM (S <= 512)
   bool use_mega = true;   // greedy decode steps of <= 64 sequences through the persistent decode_mega_kernel
   bool mega_coop = true;  // ... launched cooperatively (co-residency of its 148 CTAs guaranteed by the driver)
   bool mega_ready = false;
+  int debug_layers = -1;  // debugging: run only the first n decoder layers in the decode step (both step paths); -1 = all
   bool parity = false;
   int ks() const { return parity ? 3 : 1; }                  // K multiplier of every GEMM operand
   size_t kvb() const { return parity ? 4 : 2; }              // bytes per K/V cache element
@@ -492,7 +494,38 @@ static void launch_flash(const AttnParams& p, cudaStream_t st) {
   dim3 grid((p.S + NW * 16 - 1) / (NW * 16), p.H, p.B);
   flash_attn_kernel<NW><<<grid, NW * 32, 0, st>>>(p);
 }
+// tcgen05 attention (attention.cuh: flash_attn_tc_kernel) for sequences whose scores fit the tensor memory in one piece
+static int launch_attention_tc(gitb200_engine* h, const AttnParams& ap, cudaStream_t st) {
+  AttnTcParams p{};
+  p.out = ap.out; p.B = ap.B; p.S = ap.S; p.H = ap.H;
+  p.spad = (ap.S + 15) / 16 * 16;
+  if (p.spad <= 256) { p.kv_boxes = 1; p.kv_box_rows = p.spad; }
+  else { p.kv_boxes = 2; p.kv_box_rows = ((p.spad + 1) / 2 + 7) / 8 * 8; }
+  p.q_rows_per_batch = ap.S; p.kv_rows_per_batch = ap.S;
+  p.q_col0 = 0; p.k_col0 = 0; p.v_col0 = 0;
+  p.o_rs = ap.o_rs; p.o_bs = ap.o_bs;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  const long long rows = static_cast<long long>(ap.B) * ap.S;
+  CUtensorMap tq, tk, tv;
+  TRY(get_tmap(h, ap.q, rows, ap.H * 64, ap.q_rs, 128, &tq));
+  TRY(get_tmap(h, ap.k, rows, ap.H * 64, ap.kv_rs, p.kv_box_rows, &tk));
+  TRY(get_tmap(h, ap.v, rows, ap.H * 64, ap.kv_rs, p.kv_box_rows, &tv));
+  const size_t smem = attn_tc_smem_bytes(p.spad, p.kv_box_rows, p.kv_boxes);
+  static size_t attr_done[64] = {0};
+  if (attr_done[h->device & 63] < smem) {
+    CK(cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done[h->device & 63] = smem;
+  }
+  flash_attn_tc_kernel<<<dim3(ap.H, ap.B), kAttnTcThreads, smem, st>>>(tq, tk, tv, p);
+  CKL(h, "flash_attn_tc_kernel");
+  return 0;
+}
+
 static int launch_attention(gitb200_engine* h, const AttnParams& ap, cudaStream_t st) {
+  if (h->tc_attn && ap.S <= 512 && ap.q_bs == static_cast<long long>(ap.S) * ap.q_rs && ap.kv_bs == static_cast<long long>(ap.S) * ap.kv_rs &&
+      attn_tc_smem_bytes((ap.S + 15) / 16 * 16, ap.S <= 256 ? (ap.S + 15) / 16 * 16 : (((ap.S + 15) / 16 * 16 + 1) / 2 + 7) / 8 * 8,
+                         ap.S <= 256 ? 1 : 2) <= 226 * 1024)
+    return launch_attention_tc(h, ap, st);
   AttnParams p = ap;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   // query rows per CTA = 16 * NW: least padding first, then the larger tile (K/V are re-read per query tile)
@@ -559,7 +592,7 @@ __global__ void sum_partials_kernel(const float* __restrict__ parts, float* __re
 }
 __global__ void set_state_kernel(StepState* st, int pos, int cur_len, unsigned int* chain) {
   st->pos = pos; st->cur_len = cur_len; st->finished = 0; st->final_len = cur_len; st->step = 0;
-  st->empty_caption = 0; st->ticket = 0; st->not_eos = 0;
+  st->empty_caption = 0; st->ticket = 0; st->not_eos = 0; st->error = 0;
   for (int k = 0; k < 64; ++k) chain[k] = 0;
 }
 __global__ void init_generate_kernel(long long* tokens_out, long long* next_token, float* logprob_sum,
@@ -596,6 +629,8 @@ extern "C" int gitb200_set_option(gitb200_engine* h, const char* name, int64_t v
   if (strcmp(name, "use_chain") == 0) { h->use_chain = value != 0; return 0; }
   if (strcmp(name, "use_2cta") == 0) { h->use_2cta = value != 0; return 0; }
   if (strcmp(name, "use_mega") == 0) { h->use_mega = value != 0; return 0; }
+  if (strcmp(name, "tc_attn") == 0) { h->tc_attn = value != 0; return 0; }
+  if (strcmp(name, "debug_layers") == 0) { h->debug_layers = static_cast<int>(value); return 0; }
   if (strcmp(name, "mega_coop") == 0) { h->mega_coop = value != 0; return 0; }
   if (strcmp(name, "parity") == 0) {
     if (h->weights_from != nullptr) return fail(h, "parity: this engine borrows its weights; switch the owning engine");
@@ -1120,7 +1155,8 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
 // optional LM head -> h->logits.  Every kernel reads the position / finished flag from device state so the
 // same launch sequence (and CUDA graph) serves every step.
 static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, const int* src_row, bool lm_head) {
-  const int D = h->D, F = h->F, R = ln_.rows, nl = h->cfg.dec_layers, beam = h->cur_beam;
+  const int D = h->D, F = h->F, R = ln_.rows, beam = h->cur_beam;
+  const int nl = (h->debug_layers >= 0) ? std::min(h->debug_layers, h->cfg.dec_layers) : h->cfg.dec_layers;
   cudaStream_t st = ln_.st;
   StepState* state = h->state.as<StepState>();
   const int* skip = &state->finished;

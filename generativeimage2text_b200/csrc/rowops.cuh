@@ -17,6 +17,7 @@ struct StepState {
   int empty_caption;  // greedy step-0 special case (reference layers/decoder.py:279-291)
   unsigned int ticket;
   int not_eos;        // rows whose newest token is not EOS (per step, reset by the last block)
+  int error;          // decode_mega_kernel: a bounded wait gave up (1 grid barrier, 2 ring consumer, 3 ring producer)
 };
 
 struct LnParams {

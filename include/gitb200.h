@@ -145,6 +145,7 @@ int gitb200_generate_finish(gitb200_engine* h, int32_t* out_len_host);
 int64_t gitb200_launch_count(const gitb200_engine* h);
 /* Engine switches (defaults in parentheses): use_graph (1) CUDA-graph replay of the decode step, use_pdl (1) programmatic
  * dependent launch inside the step, use_chain (1) flag-ordered decode chain, use_2cta (1) cta_group::2 encoder GEMMs,
+ * use_mega (1) greedy decode steps of <= 64 sequences as one persistent kernel (mega_coop (1): launched cooperatively),
  * parity (0) fp32-grade verification mode: every GEMM operand is a (hi, lo) bf16 pair and each product is computed as
  * a_hi w_hi + a_lo w_hi + a_hi w_lo by the same tcgen05 kernel (three K-segments side by side), attention / K/V caches /
  * q, k, v in fp32 -- set it BEFORE gitb200_set_weight (switching it forgets the uploaded weights). */
@@ -204,6 +205,9 @@ int gitb200_preproc_run(gitb200_preproc* p, const uint8_t* src, int64_t src_byte
  * normalize_coeffs_8bpc for BICUBIC: bounds_out int32 [out_size][2] (first tap, taps), kk_out int32 [out_size][kk_cap]. */
 int gitb200_preproc_coeffs(int in_size, int out_size, int32_t* ksize_out, int32_t* bounds_out, int32_t* kk_out, int kk_cap);
 
+/* Debug: copies one decode-step work buffer of the engine ("x", "y" fp32 [rows,768]; "hb", "ctx", "qb" bf16 [rows,768];
+ * "ub" bf16 [rows,3072]) to host memory after a device synchronise.  Returns bytes copied or -1. */
+long long gitb200_debug_read(gitb200_engine* h, const char* name, void* out_host, long long max_bytes);
 /* Debug aid: in-situ timeline of the decode-step kernels. enable != 0 arms it; enable == 0 copies up to
  * max_entries (globaltimer ns, kernel id) pairs to out_host, disarms, and returns the number of entries. */
 int gitb200_debug_timeline(int enable, unsigned long long* out_host, int max_entries);

@@ -249,6 +249,28 @@ def _same_captions(a, b):
     assert torch.equal(a['logprobs'].reshape(-1), b['logprobs'].reshape(-1))
 
 
+def test_one_kernel_decode_step_matches_the_kernel_chain():
+    """Greedy batches of <= 64 run each decode step as ONE persistent kernel (decode_mega.cuh); the same call through the
+    45-launch chain (use_mega = 0) must give the same step logits up to the two paths' different bf16 roundings inside the
+    attention (the chain multiplies fp32 q with bf16 K on CUDA cores, the persistent kernel runs q.K and p.V on mma.sync)."""
+    from generativeimage2text_b200.synthetic import synthetic_state_dict, synthetic_images
+    meta = {'param': {}, 'search': 'greedy', 'max_steps': 20}
+    sd = synthetic_state_dict({}, 1, 'perturbed')
+    for rows in (64, 37, 3):
+        img = synthetic_images(rows, 0, 555 + rows).cuda()
+        m = _model(meta, sd)
+        a = m({'image': img}, return_step_logits=True)
+        forced = torch.full((rows, 20), 102, dtype=torch.long)
+        forced[:, :a['predictions'].shape[1]] = a['predictions'].cpu()
+        za = m({'image': img}, forced_tokens=forced, return_step_logits=True)['step_logits'].clone()
+        m.set_engine_option('use_mega', 0)
+        zb = m({'image': img}, forced_tokens=forced, return_step_logits=True)['step_logits'].clone()
+        torch.cuda.synchronize()
+        err = (za - zb).abs().max().item()
+        print('rows %d: one-kernel step vs kernel chain, max |dlogit| %.4f' % (rows, err))
+        assert err < 0.1
+
+
 def test_runs_are_bit_reproducible():
     """The same batch three times (fresh launches, replayed step graphs): identical tokens, logprobs and step logits."""
     from generativeimage2text_b200.synthetic import synthetic_state_dict, synthetic_images
