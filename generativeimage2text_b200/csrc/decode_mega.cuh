@@ -28,10 +28,10 @@ constexpr int kMegaThreads = (kMegaComputeWarps + 1) * 32;
 constexpr int kMegaSlots = 12;
 constexpr int kMegaSlotBytes = 16384;
 constexpr int kMegaTileBytes = 12288;      // 8 output features x 768 k x bf16, in mma-fragment order (pack_tiles_kernel)
-constexpr int kMegaKvRows = 128;           // K/V rows per ring slot (128 B per row and head)
+constexpr int kMegaKvRows = 64;            // keys per attention chunk: one ring slot = K box (8 KB) | V box (8 KB)
 constexpr int kMegaMaxRows = 64;
 constexpr int kMegaD = 768, kMegaF = 3072, kMegaH = 12;
-constexpr unsigned int kMegaSpinLimit = 1u << 27;
+constexpr unsigned int kMegaSpinLimit = 1u << 18;   // bounded waits: a protocol bug must end in an error code, not a hung device
 
 struct MegaLayer {
   const uint8_t* wqkv;     // [288] tiles: features 8t .. 8t+7 of the fused q | k | v projection
@@ -65,6 +65,7 @@ struct MegaParams {
   StepState* state;
   long long* tokens_out; int max_steps; float* logprob_sum; long long* next_token; const long long* forced;
   float* step_logits; int eos;
+  const long long* row_prefix; int row_prefix_stride; const int* row_prefix_lens;   // per-row prefixes (see SelectParams)
   unsigned int* barrier;   // [2] grid-barrier counters, used alternately by successive steps
   int* error;              // set non-zero when a bounded spin gave up (the host reports it)
 };
@@ -100,9 +101,13 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  for (unsigned int i = 0; i < kMegaSpinLimit; ++i)
+// false: gave up (or another wait already had: once the error word is set every further wait returns at once, so a broken
+// launch drains in microseconds instead of timing out chunk by chunk)
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, const int* error) {
+  for (unsigned int i = 0; i < kMegaSpinLimit; ++i) {
     if (mbar_try_wait(bar, parity)) return true;
+    if ((i & 1023u) == 1023u && *reinterpret_cast<const volatile int*>(error) != 0) return false;
+  }
   return false;
 }
 
@@ -112,15 +117,34 @@ struct MegaRing {
   uint64_t* empty;
   uint32_t idx;      // chunks consumed so far (identical in every compute warp)
   int* error;
+  volatile uint32_t* issued;   // chunks the producer has armed so far (shared memory)
   __device__ __forceinline__ const uint8_t* acquire() {
     const uint32_t slot = idx % kMegaSlots;
-    if (!mbar_wait_bounded(&full[slot], (idx / kMegaSlots) & 1)) *error = 2;
+    if (!mbar_wait_bounded(&full[slot], (idx / kMegaSlots) & 1, error)) *error = 2;
     return base + slot * kMegaSlotBytes;
   }
   __device__ __forceinline__ void release() {   // every compute warp, once per chunk
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[idx % kMegaSlots]);
     ++idx;
+  }
+  // a chunk that ONE warp consumes alone (attention items): that warp waits for it by index and frees it for all eight
+  // (A parity wait alone would be ambiguous here: the warps of a CTA walk different items, so a warp may ask for a chunk
+  //  whose slot is still two uses back.  It first waits until the producer has ARMED chunk i -- from then until this very
+  //  warp releases it, the slot's barrier can only be in chunk i's phase -- and only then for the phase to complete.)
+  __device__ __forceinline__ uint8_t* acquire_at(uint32_t i) {
+    const uint32_t slot = i % kMegaSlots;
+    unsigned int spins = 0;
+    while (*issued <= i) {
+      if (++spins > (kMegaSpinLimit << 4) || ((spins & 1023u) == 1023u && *reinterpret_cast<const volatile int*>(error) != 0)) { *error = 5; break; }
+    }
+    if (!mbar_wait_bounded(&full[slot], (i / kMegaSlots) & 1, error)) *error = 2;
+    return base + slot * kMegaSlotBytes;
+  }
+  __device__ __forceinline__ void release_at(uint32_t i) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&empty[i % kMegaSlots])), "r"(kMegaComputeWarps) : "memory");
   }
 };
 
@@ -134,7 +158,10 @@ __device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned i
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
     unsigned int spins = 0;
     while (ld_acquire_gpu(counter) < epoch) {
-      if (++spins > kMegaSpinLimit) { *error = 1; break; }
+      if (++spins > kMegaSpinLimit || ((spins & 255u) == 255u && *reinterpret_cast<const volatile int*>(error) != 0)) {
+        if (*reinterpret_cast<const volatile int*>(error) == 0) *error = 1;
+        break;
+      }
     }
     tl_mark_one(600000 + static_cast<int>(epoch / gridDim.x));      // barrier #n released
   }
@@ -190,19 +217,32 @@ __device__ __forceinline__ bool mega_combine(float (&c)[4], float* red, int buf,
   return kh == 0;
 }
 
+// Two-way variant for the LM head: both warps of a pair end up with the sum (kh0 + kh1, the same operand order in both),
+// so that each can run the statistics of ONE of the two rows a thread owns.  `red2` = [2 buffers][8 warps][32 lanes][4] floats.
+__device__ __forceinline__ void mega_combine_both(float (&c)[4], float* red2, int buf, int warp, int mt, int kh, int lane) {
+  float4* mine = reinterpret_cast<float4*>(red2) + (buf * 8 + warp) * 32 + lane;
+  const float4* other = reinterpret_cast<const float4*>(red2) + (buf * 8 + (warp ^ 4)) * 32 + lane;
+  *mine = make_float4(c[0], c[1], c[2], c[3]);
+  named_bar_sync(2 + mt, 64);
+  const float4 o = *other;
+  if (kh == 0) { c[0] += o.x; c[1] += o.y; c[2] += o.z; c[3] += o.w; }
+  else { c[0] = o.x + c[0]; c[1] = o.y + c[1]; c[2] = o.z + c[2]; c[3] = o.w + c[3]; }
+}
+
 __device__ __forceinline__ float2 ldcg_f2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMegaThreads, 1)
-decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p) {
+decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmTXT, const MegaParams p) {
   extern __shared__ __align__(1024) uint8_t mega_smem_raw[];
   uint8_t* smem = mega_smem_raw + ((1024u - (smem_u32(mega_smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;                                                  // 12 x 16 KB
-  float* red = reinterpret_cast<float*>(smem + kMegaSlots * kMegaSlotBytes);          // 2 x 4 x 32 x 4 floats = 4 KB
-  uint8_t* q_s = reinterpret_cast<uint8_t*>(red) + 4096;                 // 16 rows x 128 B (swizzled)
-  float* att_part = reinterpret_cast<float*>(q_s + 2048);                // [16 partials][68] floats
+  float* red = reinterpret_cast<float*>(smem + kMegaSlots * kMegaSlotBytes);          // 2 x 8 x 32 x 4 floats = 8 KB
+  uint8_t* q_s = reinterpret_cast<uint8_t*>(red) + 8192;                 // per compute warp: 16 rows x 128 B (swizzled)
+  float* att_part = reinterpret_cast<float*>(q_s + kMegaComputeWarps * 2048);   // scratch (LM head: this CTA's bias slice)
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(att_part) + 16 * 68 * 4);
   uint64_t* empty = full + kMegaSlots;
+  volatile uint32_t* issued = reinterpret_cast<volatile uint32_t*>(empty + kMegaSlots);
 
   StepState* st = p.state;
   if (st->finished) return;                     // stable: only the previous launch's selection phase writes it
@@ -211,6 +251,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
   const int R = p.R, M = p.M;
   const int pos = st->pos, step = st->step, cur_len = st->cur_len;
   const int n_kv = (M + kMegaKvRows - 1) / kMegaKvRows;
+  const int n_txt = pos / 64 + 1;               // 64-position boxes of the text K/V cache holding positions 0 .. pos
   const int n_items = R * kMegaH;
   const int my_cta_rev = G - 1 - cta;           // attention items are dealt from the last CTA down (those own fewer weights)
   const int n_my_items = (n_items > my_cta_rev) ? (n_items - my_cta_rev + G - 1) / G : 0;
@@ -221,11 +262,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
 
   if (tid == 0) {
     tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmTXT);
     for (int s = 0; s < kMegaSlots; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kMegaComputeWarps);
     }
     mbar_fence_init();
+    *issued = 0;
     if (cta == 0) p.barrier[(step + 1) & 1] = 0;   // the counter the NEXT step will use
   }
   __syncthreads();
@@ -236,30 +279,56 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
       uint32_t i = 0;
       auto slot_ready = [&]() -> uint8_t* {
         const uint32_t slot = i % kMegaSlots;
-        if (i >= kMegaSlots && !mbar_wait_bounded(&empty[slot], ((i / kMegaSlots) - 1) & 1)) *p.error = 3;
+        if (i >= kMegaSlots && !mbar_wait_bounded(&empty[slot], ((i / kMegaSlots) - 1) & 1, p.error)) *p.error = 3;
         return ring + slot * kMegaSlotBytes;
+      };
+      auto publish = [&]() {          // the chunk's barrier is armed: consumers may now wait for its phase
+        ++i;
+        __threadfence_block();
+        *issued = i;
       };
       auto tile = [&](const uint8_t* src) {
         uint8_t* dst = slot_ready();
         mbar_arrive_expect_tx(&full[i % kMegaSlots], kMegaTileBytes);
         bulk_load_1d(dst, src, kMegaTileBytes, &full[i % kMegaSlots]);
-        ++i;
+        publish();
       };
-      auto kv = [&](int row, int col) {
+      // one attention chunk: 64 keys of one (sequence, head): K box at the slot's start, V box 8 KB in
+      auto kv_pair = [&](const CUtensorMap* tm, int row_k, int row_v, int col) {
         uint8_t* dst = slot_ready();
         mbar_arrive_expect_tx(&full[i % kMegaSlots], kMegaSlotBytes);
-        tma_load_2d(dst, &tmKV, &full[i % kMegaSlots], col, row);
-        ++i;
+        tma_load_2d(dst, tm, &full[i % kMegaSlots], col, row_k);
+        tma_load_2d(dst + 8192, tm, &full[i % kMegaSlots], col, row_v);
+        publish();
       };
       for (int l = 0; l < p.n_layers; ++l) {
         const MegaLayer& L = p.layer[l];
         if (cta < 144) for (int j = 0; j < 2; ++j) tile(L.wqkv + static_cast<size_t>(cta * 2 + j) * kMegaTileBytes);
-        for (int k = 0; k < n_my_items; ++k) {
-          const int item = my_cta_rev + k * G;
-          const int b = item / kMegaH, h = item - b * kMegaH;
-          for (int c = 0; c < n_kv; ++c) {
-            kv((l * 2 + 0) * R * M + b * M + c * kMegaKvRows, h * 64);
-            kv((l * 2 + 1) * R * M + b * M + c * kMegaKvRows, h * 64);
+        // attention chunks of this CTA's items, ROUND-ROBIN over the items (each item is walked by its own warp, see the
+        // consumer): round r = image keys 64r .. 64r + 63 of every item, then the text rounds.  Eight items at a time.
+        for (int k0 = 0; k0 < n_my_items; k0 += kMegaComputeWarps) {
+          const int kn = min(kMegaComputeWarps, n_my_items - k0);
+          for (int r = 0; r < n_kv + n_txt; ++r) {
+            if (r == n_kv) {
+              // the text K/V of position `pos` exist once every CTA has passed barrier 7l + 1 (after this layer's QKV phase)
+              const unsigned int target = static_cast<unsigned int>(G) * (7u * l + 1u);
+              unsigned int spins = 0;
+              while (ld_acquire_gpu(p.barrier + (step & 1)) < target) {
+                if (++spins > kMegaSpinLimit || ((spins & 255u) == 255u && *reinterpret_cast<const volatile int*>(p.error) != 0)) {
+                  if (*reinterpret_cast<const volatile int*>(p.error) == 0) *p.error = 4;
+                  break;
+                }
+              }
+              asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> this thread's TMA reads
+            }
+            for (int kk = 0; kk < kn; ++kk) {
+              const int item = my_cta_rev + (k0 + kk) * G;
+              const int b = item / kMegaH, h = item - b * kMegaH;
+              if (r < n_kv)
+                kv_pair(&tmKV, (l * 2 + 0) * R * M + b * M + r * kMegaKvRows, (l * 2 + 1) * R * M + b * M + r * kMegaKvRows, h * 64);
+              else
+                kv_pair(&tmTXT, ((l * 2 + 0) * R + b) * p.T_alloc + (r - n_kv) * 64, ((l * 2 + 1) * R + b) * p.T_alloc + (r - n_kv) * 64, h * 64);
+            }
           }
         }
         if (cta < 96) tile(L.wo + static_cast<size_t>(cta) * kMegaTileBytes);
@@ -272,7 +341,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
   }
 
   // ================================== compute warps ==================================
-  MegaRing rg{ring, full, empty, 0u, p.error};
+  MegaRing rg{ring, full, empty, 0u, p.error, issued};
   unsigned int* bar = p.barrier + (step & 1);
   unsigned int epoch = 0;
   const int mt = warp & 3, kh = warp >> 2;
@@ -317,169 +386,112 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
     }
     mega_grid_sync(bar, epoch, p.error);
     // ------------------------------------------------ P2: attention ------------------------------------------------
-    // What an item needs from L2 (its query row, the text K/V rows of the caption so far) is requested one item ahead:
-    // a CTA walks 5-6 items per layer and an exposed L2 round trip per item would cost more than the item's HBM stream.
-    constexpr int kTxtPre = 5;                      // text positions per warp held in registers (8 warps x 5 = 40 positions)
-    struct AttPre { uint4 q; uint32_t kr[kTxtPre], vr[kTxtPre]; };
-    auto att_prefetch = [&](int k, AttPre& pr) {
-      pr.q = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int i = 0; i < kTxtPre; ++i) { pr.kr[i] = 0u; pr.vr[i] = 0u; }
-      if (k < n_my_items) {
+    // One WARP per (sequence, head) item: no block-level synchronisation and no cross-warp merge inside the phase.  The
+    // item's image K/V chunks and its text K/V box arrive through the ring; S = q K^T and O += P V run on mma.sync with a
+    // 16-row q tile whose row 0 is the query (rows 1..15 zero), 64 keys at a time with an online softmax.
+    {
+      const int rounds = n_kv + n_txt;                      // ring chunks per item (64 keys each), dealt round-robin
+      const uint32_t att_base = rg.idx;
+      uint8_t* qw = q_s + warp * 2048;
+      constexpr float kLog2e = 1.44269504088896340736f;
+      for (int k = warp; k < n_my_items; k += kMegaComputeWarps) {
         const int item = my_cta_rev + k * G;
         const int b = item / kMegaH, h = item - b * kMegaH;
-        if (tid < 8) pr.q = __ldcg(reinterpret_cast<const uint4*>(p.qb + static_cast<long long>(b) * kMegaD + h * 64) + tid);
-#pragma unroll
-        for (int i = 0; i < kTxtPre; ++i) {
-          const int j = warp + kMegaComputeWarps * i;
-          if (j <= pos) {
-            const long long off = (static_cast<long long>(b) * p.T_alloc + j) * kMegaD + h * 64 + 2 * lane;
-            pr.kr[i] = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_k + off));
-            pr.vr[i] = __ldcg(reinterpret_cast<const unsigned int*>(L.txt_v + off));
-          }
-        }
-      }
-    };
-    AttPre cur, nxt;
-    att_prefetch(0, cur);
-    for (int k = 0; k < n_my_items; ++k) {
-      const int item = my_cta_rev + k * G;
-      const int b = item / kMegaH, h = item - b * kMegaH;
-      att_prefetch(k + 1, nxt);
-      // q tile: row 0 = this sequence's query (already scaled by 1/8), rows 1..15 zero; 128B-swizzled like the K/V boxes
-      if (tid < 128) {
-        const int row = tid >> 3, ch = tid & 7;
-        *reinterpret_cast<uint4*>(q_s + row * 128 + ((ch ^ (row & 7)) << 4)) = (row == 0) ? cur.q : make_uint4(0, 0, 0, 0);
-      }
-      named_bar_sync(1, kMegaComputeWarps * 32);
-      uint32_t qa[4][4];
-      {
-        const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int chunk = 2 * kk + (lane >> 4);
-          ldmatrix_x4(qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], smem_u32(q_s) + row * 128 + ((chunk ^ (row & 7)) << 4));
-        }
-      }
-      float o[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f;       // row g of the q tile (only g == 0 is a real row)
-      constexpr float kLog2e = 1.44269504088896340736f;
-      for (int c = 0; c < n_kv; ++c) {
-        // ---- S = q K^T for this warp's 16 keys of the chunk ----
-        const uint32_t sK = smem_u32(rg.acquire());
-        float s[2][4];
-#pragma unroll
-        for (int jn = 0; jn < 2; ++jn) {
-          s[jn][0] = s[jn][1] = s[jn][2] = s[jn][3] = 0.f;
-          const int krow = 16 * warp + 8 * jn + (lane & 7);
-#pragma unroll
-          for (int kk2 = 0; kk2 < 2; ++kk2) {
-            const int chunk = 4 * kk2 + (lane >> 3);
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(b0, b1, b2, b3, sK + krow * 128 + ((chunk ^ (krow & 7)) << 4));
-            mma_bf16_16816(s[jn], qa[2 * kk2], b0, b1);
-            mma_bf16_16816(s[jn], qa[2 * kk2 + 1], b2, b3);
-          }
-        }
-        rg.release();
-        const int key0 = c * kMegaKvRows + 16 * warp + 2 * t;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int jn = 0; jn < 2; ++jn) {
-          if (key0 + 8 * jn >= M) s[jn][0] = -INFINITY;
-          if (key0 + 8 * jn + 1 >= M) s[jn][1] = -INFINITY;
-          mx = fmaxf(mx, fmaxf(s[jn][0], s[jn][1]));
-        }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float m_new = fmaxf(m_run, mx);
-        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // all 16 keys of this warp masked so far
-        const float corr = exp2f((m_run - m_use) * kLog2e);         // m_run == -inf -> 0
-        m_run = m_new;
-        l_run *= corr;
-        uint32_t pa[4];
-#pragma unroll
-        for (int jn = 0; jn < 2; ++jn) {
-          const float p0 = exp2f((s[jn][0] - m_use) * kLog2e);
-          const float p1 = exp2f((s[jn][1] - m_use) * kLog2e);
-          l_run += p0 + p1;
-          pa[2 * jn] = pack_bf16(p0, p1);
-          pa[2 * jn + 1] = 0u;                                      // rows 8..15 of the q tile do not exist
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
-        // ---- O += P V ----
-        const uint32_t sV = smem_u32(rg.acquire());
+        // q tile (already scaled by 1/8), 128B-swizzled like the K/V boxes: lanes 0..7 fetch row 0, everything else is zero
         {
-          const int vrow = 16 * warp + ((lane >> 3) & 1) * 8 + (lane & 7);
+          uint4 qv = make_uint4(0, 0, 0, 0);
+          if (lane < 8) qv = __ldcg(reinterpret_cast<const uint4*>(p.qb + static_cast<long long>(b) * kMegaD + h * 64) + lane);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int chunk = 2 * jj + (lane >> 4);
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4_trans(b0, b1, b2, b3, sV + vrow * 128 + ((chunk ^ (vrow & 7)) << 4));
-            mma_bf16_16816(o[2 * jj], pa, b0, b1);
-            mma_bf16_16816(o[2 * jj + 1], pa, b2, b3);
+          for (int jq = 0; jq < 4; ++jq) {
+            const int cell = lane + 32 * jq, row = cell >> 3, ch = cell & 7;
+            *reinterpret_cast<uint4*>(qw + row * 128 + ((ch ^ (row & 7)) << 4)) = (row == 0) ? qv : make_uint4(0, 0, 0, 0);
+          }
+          __syncwarp();
+        }
+        uint32_t qa[4][4];
+        {
+          const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int chunk = 2 * kk + (lane >> 4);
+            ldmatrix_x4(qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], smem_u32(qw) + row * 128 + ((chunk ^ (row & 7)) << 4));
           }
         }
-        rg.release();
-      }
-      l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-      l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-      // ---- text keys (this step's own K/V included): warp w takes positions w, w + 8, ...; lane = 2 head dims ----
-      float tm = -INFINITY, tl = 0.f, to0 = 0.f, to1 = 0.f;
-      {
-        const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(q_s + ((lane >> 2) << 4) + ((lane & 3) << 2));  // row 0: chunk ^ 0
-        const float qx = __bfloat162float(q2.x), qy = __bfloat162float(q2.y);
-        auto text_key = [&](uint32_t kr, uint32_t vr) {
-          const float sc = warp_sum(qx * bf16_lo(kr) + qy * bf16_hi(kr));
-          const float mn = fmaxf(tm, sc);
-          const float cr = exp2f((tm - mn) * kLog2e);
-          const float pe = exp2f((sc - mn) * kLog2e);
-          tl = tl * cr + pe;
-          to0 = to0 * cr + pe * bf16_lo(vr);
-          to1 = to1 * cr + pe * bf16_hi(vr);
-          tm = mn;
+        float o[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;       // row g of the q tile (only g == 0 is a real row)
+        // 64 keys: rows [row0, row0 + 64) of a K box at sK and of a V box at sV; key index = key0 + row, valid below key_end
+        auto keys64 = [&](uint32_t sK, uint32_t sV, int row0, int key0, int key_end) {
+          float sc[8][4];
+#pragma unroll
+          for (int jn = 0; jn < 8; ++jn) {
+            sc[jn][0] = sc[jn][1] = sc[jn][2] = sc[jn][3] = 0.f;
+            const int krow = row0 + 8 * jn + (lane & 7);
+#pragma unroll
+            for (int kk2 = 0; kk2 < 2; ++kk2) {
+              const int chunk = 4 * kk2 + (lane >> 3);
+              uint32_t b0, b1, b2, b3;
+              ldmatrix_x4(b0, b1, b2, b3, sK + krow * 128 + ((chunk ^ (krow & 7)) << 4));
+              mma_bf16_16816(sc[jn], qa[2 * kk2], b0, b1);
+              mma_bf16_16816(sc[jn], qa[2 * kk2 + 1], b2, b3);
+            }
+          }
+          float mx = -INFINITY;
+#pragma unroll
+          for (int jn = 0; jn < 8; ++jn) {
+            const int key = key0 + 8 * jn + 2 * t;
+            if (key >= key_end) sc[jn][0] = -INFINITY;
+            if (key + 1 >= key_end) sc[jn][1] = -INFINITY;
+            mx = fmaxf(mx, fmaxf(sc[jn][0], sc[jn][1]));
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const float m_new = fmaxf(m_run, mx);
+          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          const float corr = exp2f((m_run - m_use) * kLog2e);
+          m_run = m_new;
+          l_run *= corr;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {                  // 16 keys per k-step = score tiles 2kk, 2kk + 1
+            const float p0 = exp2f((sc[2 * kk][0] - m_use) * kLog2e), p1 = exp2f((sc[2 * kk][1] - m_use) * kLog2e);
+            const float p2 = exp2f((sc[2 * kk + 1][0] - m_use) * kLog2e), p3 = exp2f((sc[2 * kk + 1][1] - m_use) * kLog2e);
+            l_run += (p0 + p1) + (p2 + p3);
+            const uint32_t pa[4] = {pack_bf16(p0, p1), 0u, pack_bf16(p2, p3), 0u};   // rows 8..15 of the q tile do not exist
+            const int vrow = row0 + 16 * kk + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int chunk = 2 * jj + (lane >> 4);
+              uint32_t b0, b1, b2, b3;
+              ldmatrix_x4_trans(b0, b1, b2, b3, sV + vrow * 128 + ((chunk ^ (vrow & 7)) << 4));
+              mma_bf16_16816(o[2 * jj], pa, b0, b1);
+              mma_bf16_16816(o[2 * jj + 1], pa, b2, b3);
+            }
+          }
         };
-#pragma unroll
-        for (int i = 0; i < kTxtPre; ++i)
-          if (warp + kMegaComputeWarps * i <= pos) text_key(cur.kr[i], cur.vr[i]);       // warp-uniform predicate
-        for (int j = warp + kMegaComputeWarps * kTxtPre; j <= pos; j += kMegaComputeWarps) {   // captions longer than 40 tokens
-          const long long off = (static_cast<long long>(b) * p.T_alloc + j) * kMegaD + h * 64 + 2 * lane;
-          text_key(__ldcg(reinterpret_cast<const unsigned int*>(L.txt_k + off)), __ldcg(reinterpret_cast<const unsigned int*>(L.txt_v + off)));
+        // chunk (item k, round r) sits at  att_base + [items before this group of eight] * rounds + r * kn + (k % 8)
+        const int k0 = k - warp, kn = min(kMegaComputeWarps, n_my_items - k0);
+        const uint32_t c0 = att_base + static_cast<uint32_t>(k0) * rounds + warp;
+        for (int r = 0; r < rounds; ++r) {
+          const uint32_t ci = c0 + static_cast<uint32_t>(r) * kn;
+          const uint32_t sK = smem_u32(rg.acquire_at(ci));
+          if (r < n_kv) keys64(sK, sK + 8192, 0, r * kMegaKvRows, M);               // image keys 64r ..
+          else keys64(sK, sK + 8192, 0, (r - n_kv) * 64, pos + 1);                 // text positions 64(r - n_kv) ..
+          rg.release_at(ci);
         }
-      }
-      // ---- merge the 16 partial softmax states (8 image-key partials, 8 text-key partials) ----
-      if (g == 0) {
-        float* pp = att_part + warp * 68;
-        if (t == 0) { pp[64] = m_run; pp[65] = l_run; }
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+        if (g == 0) {
+          const float inv = 1.0f / l_run;
+          __nv_bfloat16* dst = p.ctx + static_cast<long long>(b) * kMegaD + h * 64 + 2 * t;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { pp[8 * j + 2 * t] = o[j][0]; pp[8 * j + 2 * t + 1] = o[j][1]; }
-      }
-      {
-        float* pp = att_part + (8 + warp) * 68;
-        if (lane == 0) { pp[64] = tm; pp[65] = tl; }
-        pp[2 * lane] = to0;
-        pp[2 * lane + 1] = to1;
-      }
-      named_bar_sync(1, kMegaComputeWarps * 32);
-      if (tid < 64) {
-        float mm = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mm = fmaxf(mm, att_part[i * 68 + 64]);
-        float lsum = 0.f, acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float mi = att_part[i * 68 + 64];
-          const float w = (mi == -INFINITY) ? 0.f : exp2f((mi - mm) * kLog2e);
-          lsum += att_part[i * 68 + 65] * w;
-          acc += att_part[i * 68 + tid] * w;
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16(o[j][0] * inv, o[j][1] * inv);
         }
-        p.ctx[static_cast<long long>(b) * kMegaD + h * 64 + tid] = __float2bfloat16_rn(acc / lsum);
+        __syncwarp();                                       // the q tile is rewritten by this warp's next item
       }
-      named_bar_sync(1, kMegaComputeWarps * 32);      // q_s / att_part are rewritten by the next item
-      cur = nxt;
+      rg.idx = att_base + static_cast<uint32_t>(n_my_items) * rounds;
     }
     mega_grid_sync(bar, epoch, p.error);
     // ------------------------------------------------ P3: attention output projection (+bias +residual) ------------------
@@ -623,15 +635,19 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
   }
 
   // ------------------------------------------------ LM head with the greedy statistics folded in ---------------------------
-  // Each kh = 0 warp keeps, for its 2 x 2 (row, column-parity) positions, the running (max, arg max, sum exp) over this
-  // CTA's features -- the logits themselves never leave the SM (unless the parity hook asks for them).
+  // After the two K halves of a tile are summed, the kh = 0 warp of a pair keeps the statistics of row g, the kh = 1 warp
+  // those of row g + 8: for its row and its 2 columns per tile a thread maintains the running (max, arg max, sum exp) over
+  // this CTA's features -- the logits themselves never leave the SM (unless the parity hook asks for them).
   {
-    const bool first = (step == 0);
-    long long last0 = -1, last1 = -1;
-    if (r0 < R) last0 = p.next_token[r0];
-    if (r1 < R) last1 = p.next_token[r1];
-    float smax[2] = {-INFINITY, -INFINITY}, ssum[2] = {0.f, 0.f};
-    int sarg[2] = {0x7fffffff, 0x7fffffff};
+    const int my_row = kh ? r1 : r0;
+    long long last = -1;
+    bool first = (step == 0);                       // no no-repeat mask at a row's first real decision
+    if (my_row < R) {
+      last = p.next_token[my_row];
+      if (p.row_prefix != nullptr) first = cur_len <= p.row_prefix_lens[my_row];
+    }
+    float smax = -INFINITY, ssum = 0.f;
+    int sarg = 0x7fffffff;
     float* bias_s = att_part;                       // this CTA's slice of the output bias (<= 8 * lm_per floats)
     for (int i = tid; i < lm_n * 8; i += kMegaComputeWarps * 32) {
       const int col = lm_t0 * 8 + i;
@@ -646,56 +662,45 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
         const uint8_t* tb = rg.acquire();
         mega_mma_tile(c, a, tb, kh, lane);
         rg.release();
-        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+        mega_combine_both(c, red, red_buf, warp, mt, kh, lane);
+        red_buf ^= 1;
+        if (my_row < R) {
           const int f = (lm_t0 + j) * 8 + 2 * t;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int r = hh ? r1 : r0;
-            if (r >= R) continue;
-            const long long last = hh ? last1 : last0;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = f + e;
-              if (col >= p.V) continue;
-              float v = c[2 * hh + e] + bias_s[j * 8 + 2 * t + e];
-              if (p.step_logits != nullptr) p.step_logits[(static_cast<long long>(step) * R + r) * p.V + col] = v;
-              if (!first && col == static_cast<int>(last)) v = -10000.0f;        // no-repeat (reference :330)
-              if (v > smax[hh]) {            // columns arrive in increasing order: the lowest index wins exact ties
-                ssum[hh] = ssum[hh] * __expf(smax[hh] - v) + 1.0f;
-                smax[hh] = v;
-                sarg[hh] = col;
-              } else {
-                ssum[hh] += __expf(v - smax[hh]);
-              }
+          for (int e = 0; e < 2; ++e) {
+            const int col = f + e;
+            if (col >= p.V) continue;
+            float v = c[2 * kh + e] + bias_s[j * 8 + 2 * t + e];
+            if (p.step_logits != nullptr) p.step_logits[(static_cast<long long>(step) * R + my_row) * p.V + col] = v;
+            if (!first && col == static_cast<int>(last)) v = -10000.0f;        // no-repeat (reference :330)
+            if (v > smax) {            // columns arrive in increasing order: the lowest index wins exact ties
+              ssum = ssum * __expf(smax - v) + 1.0f;
+              smax = v;
+              sarg = col;
+            } else {
+              ssum += __expf(v - smax);
             }
           }
         }
-        red_buf ^= 1;
       }
     }
-    if (kh == 0) {
-      // combine the 4 lanes of a quad (they hold the same rows, interleaved column pairs)
+    // combine the 4 lanes of a quad (they hold the same row, interleaved column pairs)
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-        for (int o2 = 1; o2 <= 2; o2 <<= 1) {
-          const float m_o = __shfl_xor_sync(0xffffffffu, smax[hh], o2);
-          const float s_o = __shfl_xor_sync(0xffffffffu, ssum[hh], o2);
-          const int a_o = __shfl_xor_sync(0xffffffffu, sarg[hh], o2);
-          const float mn = fmaxf(smax[hh], m_o);
-          const float sa = (smax[hh] == -INFINITY) ? 0.f : __expf(smax[hh] - mn);
-          const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - mn);
-          ssum[hh] = ssum[hh] * sa + s_o * sb;
-          if (m_o > smax[hh] || (m_o == smax[hh] && a_o < sarg[hh])) sarg[hh] = a_o;
-          smax[hh] = mn;
-        }
-        const int r = hh ? r1 : r0;
-        if (t == 0 && r < R) {
-          p.part_max[static_cast<long long>(r) * G + cta] = smax[hh];
-          p.part_sum[static_cast<long long>(r) * G + cta] = ssum[hh];
-          p.part_arg[static_cast<long long>(r) * G + cta] = sarg[hh];
-        }
-      }
+    for (int o2 = 1; o2 <= 2; o2 <<= 1) {
+      const float m_o = __shfl_xor_sync(0xffffffffu, smax, o2);
+      const float s_o = __shfl_xor_sync(0xffffffffu, ssum, o2);
+      const int a_o = __shfl_xor_sync(0xffffffffu, sarg, o2);
+      const float mn = fmaxf(smax, m_o);
+      const float sa = (smax == -INFINITY) ? 0.f : __expf(smax - mn);
+      const float sb = (m_o == -INFINITY) ? 0.f : __expf(m_o - mn);
+      ssum = ssum * sa + s_o * sb;
+      if (m_o > smax || (m_o == smax && a_o < sarg)) sarg = a_o;
+      smax = mn;
+    }
+    if (t == 0 && my_row < R) {
+      p.part_max[static_cast<long long>(my_row) * G + cta] = smax;
+      p.part_sum[static_cast<long long>(my_row) * G + cta] = ssum;
+      p.part_arg[static_cast<long long>(my_row) * G + cta] = sarg;
     }
   }
   mega_grid_sync(bar, epoch, p.error);
@@ -703,7 +708,9 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
   // ------------------------------------------------ selection (greedy bookkeeping) + next token's embedding ----------------
   if (cta < R && warp == 0) {
     const int row = cta;
-    const bool first = (step == 0);
+    const int own_prefix = (p.row_prefix != nullptr) ? p.row_prefix_lens[row] : 0;
+    const bool in_prefix = (p.row_prefix != nullptr) && cur_len < own_prefix;
+    const bool first = (p.row_prefix != nullptr) ? (cur_len == own_prefix) : (step == 0);
     float gm = -INFINITY, gs = 0.f;
     int ga = 0x7fffffff;
     for (int k = lane; k < G; k += 32) {           // increasing CTA order = increasing column order
@@ -730,9 +737,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
       gm = mn;
     }
     const long long last = p.next_token[row];
-    const bool row_done = (!first) && (last == p.eos);
+    const bool row_done = (!first) && (!in_prefix) && (last == p.eos);
     long long tok = row_done ? p.eos : ga;                         // EOS forcing: one-hot distribution, log-prob 0
-    const float lp = row_done ? 0.f : -logf(gs);
+    float lp = row_done ? 0.f : -logf(gs);
+    if (in_prefix) {                                               // still feeding this row's prefix
+      tok = p.row_prefix[static_cast<long long>(row) * p.row_prefix_stride + cur_len];
+      lp = 0.f;
+    }
     long long nxt = tok;
     if (p.forced != nullptr) nxt = p.forced[static_cast<long long>(row) * p.max_steps + cur_len];
     if (lane == 0) {
@@ -791,7 +802,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
         st->step = step + 1;
         if (not_eos == 0) {
           st->finished = 1;
-          if (first) st->empty_caption = 1;
+          if (step == 0 && p.row_prefix == nullptr) st->empty_caption = 1;
         }
         if (cur_len + 1 >= p.max_steps) st->finished = 1;
         __threadfence();
@@ -800,6 +811,6 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const MegaParams p)
   }
 }
 
-constexpr size_t kMegaSmemBytes = 1024 + kMegaSlots * kMegaSlotBytes + 4096 + 2048 + 16 * 68 * 4 + 2 * kMegaSlots * 8 + 64;
+constexpr size_t kMegaSmemBytes = 1024 + kMegaSlots * kMegaSlotBytes + 8192 + kMegaComputeWarps * 2048 + 16 * 68 * 4 + 2 * kMegaSlots * 8 + 64 + 64;
 
 }  // namespace gitb200

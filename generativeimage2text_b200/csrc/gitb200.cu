@@ -39,7 +39,7 @@
 using namespace gitb200;
 typedef __nv_bfloat16 bf16;
 
-#define GITB200_ABI_VERSION 3
+#define GITB200_ABI_VERSION 4
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -173,6 +173,10 @@ struct gitb200_engine {
   bool pend_beam = false;
   cudaStream_t pend_stream = nullptr;
   cudaEvent_t chunk_ev[2] = {nullptr, nullptr};   // decode-loop chunks (generate_impl)
+  // per-row prefixes of the NEXT generate call (gitb200_set_row_prefixes; consumed by that call)
+  const int64_t* rp_tok = nullptr;
+  const int32_t* rp_lens = nullptr;
+  int rp_rows = 0, rp_stride = 0;
   int64_t* pend_tok_host = nullptr;  // host-buffer variant: results land here
 };
 
@@ -596,11 +600,12 @@ __global__ void set_state_kernel(StepState* st, int pos, int cur_len, unsigned i
   for (int k = 0; k < 64; ++k) chain[k] = 0;
 }
 __global__ void init_generate_kernel(long long* tokens_out, long long* next_token, float* logprob_sum,
-                                     const long long* prefix, int P, int rows, int max_steps, int sos) {
+                                     const long long* prefix, int P, int rows, int max_steps, int sos, long long prefix_row_stride) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  for (int i = 0; i < P; ++i) tokens_out[static_cast<long long>(r) * max_steps + i] = prefix ? prefix[i] : sos;
-  next_token[r] = prefix ? prefix[0] : sos;
+  const long long* pr = prefix ? prefix + r * prefix_row_stride : nullptr;   // stride 0: one prefix for all rows
+  for (int i = 0; i < P; ++i) tokens_out[static_cast<long long>(r) * max_steps + i] = pr ? pr[i] : sos;
+  next_token[r] = pr ? pr[0] : sos;
   logprob_sum[r] = 0.f;
 }
 __global__ void advance_prefix_kernel(StepState* st, long long* next_token, const long long* prefix, int idx, int rows,
@@ -1080,7 +1085,14 @@ static int prefill_impl(gitb200_engine* h, int B, int beam, int T_alloc, float* 
   CK(h->pctx.ensure(rows * D * 2 * ks));
   CK(h->pu.ensure(rows * F * 2 * ks));
   CK(h->img_kv.ensure(static_cast<long long>(nl) * 2 * rows * D * kvb));
-  CK(h->txt_kv.ensure(static_cast<long long>(nl) * 2 * R * T_alloc * D * kvb));
+  {
+    // decode_mega_kernel fetches whole 64-position boxes of the text cache and masks the positions past the caption's end
+    // by giving them probability 0 -- which only works if what lies there is finite: a fresh allocation is zeroed once
+    // (afterwards the buffer only ever holds K/V values or zeros)
+    const void* before = h->txt_kv.p;
+    CK(h->txt_kv.ensure(static_cast<long long>(nl) * 2 * R * T_alloc * D * kvb));
+    if (h->txt_kv.p != before) CK(cudaMemsetAsync(h->txt_kv.p, 0, h->txt_kv.cap, st));
+  }
   CK(h->src_row[0].ensure(static_cast<size_t>(R) * T_alloc * 4));
   CK(h->src_row[1].ensure(static_cast<size_t>(R) * T_alloc * 4));
   CK(h->xd_t.ensure(static_cast<size_t>(R) * D * 4));

@@ -386,7 +386,13 @@ struct SelectParams {
   const long long* forced;  // [rows, max_steps] or null
   StepState* state;
   float* step_logits;       // optional dump [steps, rows_total, V]
-  int rows_total, row0;     // this launch covers rows [row0, row0 + rows) of the batch (decode lanes)
+  int rows_total, row0;     // this launch covers rows [row0, row0 + rows) of the batch
+  // per-row prefixes (question batches, an extension of the reference's single-prefix path layers/decoder.py:985-1006):
+  // row r starts from row_prefix[r * stride + 0 .. lens[r]); all rows advance in lockstep from text position 0, and while a
+  // row is still inside its prefix its selection is overridden by the next prefix token (log-prob 0, no bookkeeping)
+  const long long* row_prefix;
+  int row_prefix_stride;
+  const int* row_prefix_lens;
   // per-row partial results of the vocabulary slices (grid.x = n_split CTAs per row)
   int n_split;
   float* part_max;          // [rows, n_split]
@@ -419,7 +425,9 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
   // The input token of this step (== our previous choice unless teacher forcing is on): the reference's
   // masks are functions of the *input* sequence (predictions_so_far[:, -1]).
   const long long last = p.next_token[row];
-  const bool first = (step == 0);
+  const int own_prefix = (p.row_prefix != nullptr) ? p.row_prefix_lens[p.row0 + row] : 0;
+  const bool in_prefix = (p.row_prefix != nullptr) && cur_len < own_prefix;
+  const bool first = (p.row_prefix != nullptr) ? (cur_len == own_prefix) : (step == 0);   // the row's first real decision
   const int chunk = (p.V + p.n_split - 1) / p.n_split;
   const int lo = split * chunk;
   const int hi = min(p.V, lo + chunk);
@@ -497,10 +505,13 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
         if (pm > gm) ga = pa;
         gm = mn;
       }
-      const bool row_done = (!first) && (last == p.eos);
+      const bool row_done = (!first) && (!in_prefix) && (last == p.eos);
       long long tok;
       float lp;
-      if (row_done) {  // one-hot EOS distribution (reference :347-351): log_softmax gives exactly 0 at EOS
+      if (in_prefix) {   // still feeding this row's prefix: the next prefix token, nothing to score
+        tok = p.row_prefix[static_cast<long long>(p.row0 + row) * p.row_prefix_stride + cur_len];
+        lp = 0.f;
+      } else if (row_done) {  // one-hot EOS distribution (reference :347-351): log_softmax gives exactly 0 at EOS
         tok = p.eos;
         lp = 0.f;
       } else {
@@ -527,7 +538,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
         st->step = step + 1;
         if (not_eos == 0) {
           st->finished = 1;
-          if (first) st->empty_caption = 1;
+          if (step == 0 && p.row_prefix == nullptr) st->empty_caption = 1;
         }
         if (cur_len + 1 >= p.max_steps) st->finished = 1;
         // every CTA of every kernel of this step has passed its wait: recycle the chain counters
@@ -541,9 +552,10 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const SelectParams p
 
 // logprobs / num_valid (reference layers/decoder.py:433-438) and EOS padding of the unused tail.
 __global__ void greedy_finalize_kernel(long long* tokens_out, const float* logprob_sum, float* logprobs_out, int rows,
-                                       int max_steps, int prefix_len, int eos, const StepState* state) {
+                                       int max_steps, int prefix_len, int eos, const StepState* state, const int* row_prefix_lens) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
+  if (row_prefix_lens != nullptr) prefix_len = row_prefix_lens[row];
   const int n = state->final_len;
   for (int i = n; i < max_steps; ++i) tokens_out[static_cast<long long>(row) * max_steps + i] = eos;
   int not_eos = 0, has_eos = 0;

@@ -57,6 +57,10 @@ struct BeamParams {
   long long* next_token;  // [rows]
   StepState* state;
   float* step_logits;     // optional dump [steps, rows, V]
+  // per-image prefixes (see SelectParams): image b starts from row_prefix[b * stride + 0 .. lens[b])
+  const long long* row_prefix;
+  int row_prefix_stride;
+  const int* row_prefix_lens;
 };
 
 __device__ __forceinline__ float beam_length_norm(int length, float lp) {
@@ -156,7 +160,16 @@ __global__ void __launch_bounds__(32) beam_update_kernel(const BeamParams p) {
   __shared__ int n_row[kMaxBeam];   // next beams: source row (global)
   __shared__ int n_word[kMaxBeam];
   __shared__ float n_score[kMaxBeam];
-  if (lane == 0) {
+  const bool in_prefix = (p.row_prefix != nullptr) && cur_len < p.row_prefix_lens[b];
+  if (lane == 0 && in_prefix) {
+    // the image is still inside its prefix: every beam takes the next prefix token, scores and histories stay as they are
+    for (int k = 0; k < beam; ++k) {
+      n_row[k] = b * beam + k;
+      n_word[k] = static_cast<int>(p.row_prefix[static_cast<long long>(b) * p.row_prefix_stride + cur_len]);
+      n_score[k] = p.s.beam_scores[b * beam + k];
+    }
+  }
+  if (lane == 0 && !in_prefix) {
     // merge the `beam` row lists into the image's top-NC, ordered by (value desc, flat index asc)
     int ptr[kMaxBeam];
     for (int k = 0; k < beam; ++k) ptr[k] = 0;
@@ -257,14 +270,15 @@ __global__ void __launch_bounds__(32) beam_update_kernel(const BeamParams p) {
 }
 
 __global__ void beam_init_kernel(BeamState s, long long* next_token, const long long* prefix, int P, int sos, int B,
-                                 int beam, int max_steps, int T_alloc) {
+                                 int beam, int max_steps, int T_alloc, long long prefix_row_stride) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int rows = B * beam;
   if (r == 0) *s.cur = 0;
   if (r < rows) {
     s.beam_scores[r] = (r % beam == 0) ? 0.f : -1e9f;  // reference :1118-1120
-    for (int i = 0; i < P; ++i) s.ids[0][static_cast<long long>(r) * max_steps + i] = prefix ? prefix[i] : sos;
-    next_token[r] = prefix ? prefix[0] : sos;
+    const long long* pr = prefix ? prefix + (r / beam) * prefix_row_stride : nullptr;   // stride 0: one prefix for all rows
+    for (int i = 0; i < P; ++i) s.ids[0][static_cast<long long>(r) * max_steps + i] = pr ? pr[i] : sos;
+    next_token[r] = pr ? pr[0] : sos;
     for (int j = 0; j < T_alloc; ++j) { s.src[0][r * T_alloc + j] = r; s.src[1][r * T_alloc + j] = r; }
   }
   if (r < B) { s.done[r] = 0; s.hyp_score[r] = -1e30f; s.worst_score[r] = 1e9f; s.hyp_len[r] = 0; }

@@ -380,11 +380,27 @@ def test_git_inference_single_tsv(image_tsv, model_name, question_tsv, out_tsv, 
             q_key, q_info = question_tsv[i][:2]
             assert image_key == q_key
             img = transforms(pilimg_from_base64(image_col)).unsqueeze(0)
-            for q in json.loads(q_info):
-                input_ids = _prefix_ids(tokenizer, q['question'])
+            questions = json.loads(q_info)
+            ids = [_prefix_ids(tokenizer, q['question']) for q in questions]
+            if len(questions) > 1 and max(len(i) for i in ids) < model.decoder.max_steps:
+                # all questions of an image in ONE call (one prefix per row; the reference loops with batch 1,
+                # inference.py:201-212): each row is generated exactly as its own batch-1 call would be
+                width = max(len(i) for i in ids)
+                pad = torch.zeros((len(ids), width), dtype=torch.long)
+                for r, i in enumerate(ids):
+                    pad[r, :len(i)] = torch.tensor(i)
                 with torch.no_grad():
-                    result = model({'image': img, 'prefix': torch.tensor(input_ids).unsqueeze(0).cuda()})
-                answer = tokenizer.decode(result['predictions'][0].tolist(), skip_special_tokens=True)
+                    result = model({'image': img.expand(len(ids), -1, -1, -1), 'prefix': pad.cuda(),
+                                    'prefix_len': torch.tensor([len(i) for i in ids])})
+                preds = result['predictions'].tolist()
+            else:
+                preds = []
+                for input_ids in ids:
+                    with torch.no_grad():
+                        result = model({'image': img, 'prefix': torch.tensor(input_ids).unsqueeze(0).cuda()})
+                    preds.append(result['predictions'][0].tolist())
+            for q, p in zip(questions, preds):
+                answer = tokenizer.decode(p, skip_special_tokens=True)
                 yield json_dump({'answer': answer, 'question_id': q['question_id']}),
 
     gen_rows = question_rows if question_tsv else caption_rows

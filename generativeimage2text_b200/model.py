@@ -60,8 +60,9 @@ class GeneratorWithBeamSearch(object):
 class _Pending(object):
     """Handle of an enqueued `model(batch)` (see GitB200CaptioningModel.submit)."""
 
-    def __init__(self, model, slot, sp, P, tokens, logprobs, step_logits, keep):
+    def __init__(self, model, slot, sp, P, tokens, logprobs, step_logits, keep, row_lens=None):
         self.model, self.slot, self.sp, self.P = model, slot, sp, P
+        self.row_lens = row_lens          # per-row prefix lengths (host list) of a prefix batch
         self.tokens, self.logprobs, self.step_logits, self._keep = tokens, logprobs, step_logits, keep
         self._out = None
 
@@ -357,6 +358,7 @@ class GitB200CaptioningModel(nn.Module):
         """`model(batch)` of the reference in eval mode: CaptioningModel.forward -> infer.
 
         batch: {'image': FloatTensor[B,3,H,W] | [FloatTensor[B,3,H,W]] * frames, 'prefix'?: LongTensor[1,P]}
+               (extension: 'prefix': LongTensor[B,P] + optional 'prefix_len': [B] = one prefix per image)
         forced_tokens / return_step_logits are parity-test hooks (teacher forcing, raw per-step logits).
         """
         return self.submit(batch, forced_tokens, return_step_logits, slot=0, _caller_stream=True).result()
@@ -377,7 +379,7 @@ class GitB200CaptioningModel(nn.Module):
         if 'context' in batch:
             raise NotImplementedError("'context' batches are not produced by the reference inference path")
         if (int(coalesce) > 1 and slot is None and not _caller_stream and forced_tokens is None and not return_step_logits
-                and 'prefix' not in batch):
+                and 'prefix' not in batch and 'prefix_len' not in batch):
             return self._submit_coalesced(batch['image'], depth, int(coalesce))
         if self._open_group is not None:
             self._open_group.launch()         # keep the submission order
@@ -404,10 +406,26 @@ class GitB200CaptioningModel(nn.Module):
             stream.wait_stream(cur)           # inputs produced on the caller's stream
         sp = self._search_struct()
         prefix, P = None, 0
-        if 'prefix' in batch:
+        row_prefix, row_lens_dev, row_lens = None, None, None
+        if 'prefix' in batch and B > 1 and len(batch['prefix']) == B:
+            # one prefix per image (question batches) -- beyond the reference, which asserts a single prefix and batch 1
+            # (layers/decoder.py:985-989): row r is generated exactly as a batch-1 call with batch['prefix'][r, :len_r]
+            row_prefix = batch['prefix'].to(device=dev, dtype=torch.long).contiguous()
+            if row_prefix.dim() != 2:
+                raise ValueError("a per-image 'prefix' must be a [B, P] tensor")
+            if 'prefix_len' in batch:
+                row_lens = [int(v) for v in batch['prefix_len']]
+            else:
+                row_lens = [row_prefix.shape[1]] * B
+            if len(row_lens) != B or min(row_lens) < 1 or max(row_lens) > row_prefix.shape[1] or max(row_lens) >= sp.max_steps:
+                raise ValueError("'prefix_len' must hold B lengths in [1, P] below the decoder's max_steps")
+            if forced_tokens is not None:
+                raise ValueError('teacher forcing is not available for per-image prefixes')
+            row_lens_dev = torch.tensor(row_lens, dtype=torch.int32, device=dev)
+        elif 'prefix' in batch:
             assert len(batch['prefix']) == 1, 'not supported'      # reference layers/decoder.py:988
             if B != 1:
-                raise AssertionError('not supported: a prefix needs batch size 1')
+                raise AssertionError('not supported: one shared prefix needs batch size 1 (pass a [B, P] prefix for one per image)')
             prefix = batch['prefix'].to(device=dev, dtype=torch.long).contiguous().view(-1)
             P = prefix.numel()
         tokens = torch.empty((B, sp.max_steps), dtype=torch.long, device=dev)
@@ -420,18 +438,21 @@ class GitB200CaptioningModel(nn.Module):
         if return_step_logits:
             rows = B * (sp.beam_size if sp.mode == _lib.SEARCH_BEAM else 1)
             step_logits = torch.zeros((sp.max_steps - max(P, 1), rows, VOCAB), dtype=torch.float32, device=dev)
-        for t in (x, prefix, forced):
+        for t in (x, prefix, forced, row_prefix, row_lens_dev):
             if t is not None and stream is not cur:
                 t.record_stream(stream)
         # inputs of another size than test_crop_size (MinMaxResizeForTest, reference inference.py:29-64): the engine
         # re-samples the positional embedding to their patch grid (reference layers/CLIP/model.py:245-251)
         _lib.check(lib.gitb200_set_input_size(eng, int(x.shape[-2]), int(x.shape[-1])), eng, 'set_input_size')
+        if row_prefix is not None:
+            _lib.check(lib.gitb200_set_row_prefixes(eng, row_prefix.data_ptr(), B, int(row_prefix.shape[1]), row_lens_dev.data_ptr()),
+                       eng, 'set_row_prefixes')
         _lib.check(lib.gitb200_generate_async(
             eng, x.data_ptr(), B, frames, prefix.data_ptr() if prefix is not None else None, P,
             ctypes.byref(sp), forced.data_ptr() if forced is not None else None, tokens.data_ptr(),
             logprobs.data_ptr(), step_logits.data_ptr() if step_logits is not None else None,
             stream.cuda_stream), eng, 'generate')
-        pend = _Pending(self, slot, sp, P, tokens, logprobs, step_logits, (x, prefix, forced))
+        pend = _Pending(self, slot, sp, P, tokens, logprobs, step_logits, (x, prefix, forced, row_prefix, row_lens_dev), row_lens)
         sl['pending'] = pend
         return pend
 
@@ -471,6 +492,18 @@ class GitB200CaptioningModel(nn.Module):
         sl['pending'] = None
         sp, P, tokens, logprobs = pend.sp, pend.P, pend.tokens, pend.logprobs
         n = out_len.value
+        if pend.row_lens is not None:
+            # per-image prefixes: row r = what a batch-1 call with its prefix returns (prefix stripped), EOS-padded to the
+            # longest row; greedy width as the reference's loop would leave it for the rows together
+            full = tokens[:, :n] if sp.mode == _lib.SEARCH_GREEDY else tokens
+            width = full.shape[1] - min(pend.row_lens)
+            pred = torch.full((full.shape[0], width), self.eos_index, dtype=torch.long, device=full.device)
+            for r, pl in enumerate(pend.row_lens):
+                pred[r, :full.shape[1] - pl] = full[r, pl:]
+            out = {'predictions': pred, 'logprobs': logprobs if sp.mode == _lib.SEARCH_GREEDY else logprobs[:, None]}
+            if pend.step_logits is not None:
+                out['step_logits'] = pend.step_logits
+            return out
         if sp.mode == _lib.SEARCH_GREEDY:
             if n < 0:   # every first token was EOS (reference layers/decoder.py:279-291)
                 warnings.warn('Empty captions predicted. You may want to increase beam size or ensure your step '

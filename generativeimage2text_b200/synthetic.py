@@ -156,14 +156,19 @@ def synthetic_state_dict(param=None, seed=0, variant='init'):
             # sharper decoder attention (q, k x8) whose output weighs more in the residual stream (x4): the ranking of
             # the live tokens then depends on WHICH image tokens a row attends to, i.e. on the image and the history
             if key.endswith('attention.self.query.weight') or key.endswith('attention.self.key.weight'):
-                a = a * np.float32(8.0)
+                a = a * np.float32(DECISIVE_QK_SCALE)
             elif key.endswith('attention.output.dense.weight'):
-                a = a * np.float32(4.0)
+                a = a * np.float32(DECISIVE_AO_SCALE)
         sd[key] = torch.from_numpy(np.ascontiguousarray(a))
     return sd
 
 
 DECISIVE_LIVE = 8      # tokens that stay in play in the 'decisive' variant (EOS is one of them)
+# decoder attention sharpening of the 'decisive' variant (q, k weights / attention output weights).  Chosen on B200 with
+# tools/decisive_pick.py: the sharper the softmax the more the captions depend on the image -- and the more bf16 rounding is
+# amplified; x8 / x4 made the decoder chaotic (12.5 max logit error), these values keep the error at the random-init level
+DECISIVE_QK_SCALE = 2.0
+DECISIVE_AO_SCALE = 2.0
 
 
 def decisive_output_bias(bias, seed):

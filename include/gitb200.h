@@ -141,6 +141,13 @@ int gitb200_generate_host_async(gitb200_engine* h, const float* images_host, int
                                 int64_t* tokens_out_host, float* logprobs_out_host, void* stream);
 int gitb200_generate_finish(gitb200_engine* h, int32_t* out_len_host);
 
+/* Per-row prefixes for the NEXT generate call (question batches; the reference allows one prefix and batch 1 only,
+ * layers/decoder.py:985-1006): prefix_dev int64 [rows, stride], lens_dev int32 [rows] (1 <= len <= stride, len < max_steps;
+ * tokens past a row's length are ignored).  rows must equal that call's batch; pass prefix_len = 0 to it.  Every row is
+ * generated exactly as a batch-1 call with its own prefix would be; tokens_out rows hold prefix + generated tokens.  The
+ * buffers must stay valid until the call has finished. */
+int gitb200_set_row_prefixes(gitb200_engine* h, const int64_t* prefix_dev, int rows, int stride, const int32_t* lens_dev);
+
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t gitb200_launch_count(const gitb200_engine* h);
 /* Engine switches (defaults in parentheses): use_graph (1) CUDA-graph replay of the decode step, use_pdl (1) programmatic

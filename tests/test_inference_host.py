@@ -77,3 +77,21 @@ def test_row_formats():
     assert inf.json_dump([{'caption': 'a b'}]) == '[{"caption":"a b"}]'
     assert inf.json_dump({'question_id': 3, 'answer': 'x'}) == '{"answer":"x","question_id":3}'
     assert inf.pilimg_from_base64('!!!not base64!!!') is None
+
+
+def test_yaml_base_is_merged_per_path(tmp_path):
+    """`_base_` files are merged path by path like the reference's load_from_yaml_file (tsv_io.py:97-107): a child that
+    overrides one nested key keeps the rest of the base's sub-dictionary."""
+    from generativeimage2text_b200.inference import load_from_yaml_file
+    (tmp_path / 'base.yaml').write_text('param:\n  a: 1\n  b: {c: 2, d: 3}\nname: base\nlst: [1, 2]\n')
+    (tmp_path / 'child.yaml').write_text('_base_: base.yaml\nparam:\n  b: {c: 20}\nlst: [9]\n')
+    got = load_from_yaml_file(str(tmp_path / 'child.yaml'))
+    assert got == {'param': {'a': 1, 'b': {'c': 20, 'd': 3}}, 'name': 'base', 'lst': [9]}
+
+
+def test_respect_ratio_key_presence_selects_the_transform():
+    """The reference tests `'test_respect_ratio_max' in param` (inference.py:113), not the value's truthiness."""
+    from generativeimage2text_b200.inference import ImageTransform
+    assert ImageTransform({'test_crop_size': 160}, device='cpu').minmax is None
+    assert ImageTransform({'test_crop_size': 160, 'test_respect_ratio_max': 224}, device='cpu').minmax is not None
+    assert ImageTransform({'test_crop_size': 160, 'test_respect_ratio_max': 0}, device='cpu').minmax is not None
