@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(NW * 32) flash_attn_kernel(const AttnParams p)
 //   shared memory in the K-major swizzled operand layout -> tcgen05.mma O = P V with V as an MN-major B operand (V stays
 //   [key][dim] as TMA delivered it), O overwriting TMEM columns [0, 64) -> the softmax warps scale by 1 / row sum and
 //   store bf16 rows.
-//   Warp 0: TMA + MMA issue (one lane); warps 1-4: softmax / epilogue (TMEM lane quadrants 1, 2, 3, 0).
+//   Warp 0: TMA + MMA issue (one lane); warps 1-8: softmax / epilogue, two per TMEM lane quadrant (they split the key
+//   columns).  Q and K share shared memory with P (K is re-fetched per query tile -- an L2 hit), which keeps a CTA at
+//   ~92 KB for S = 197 so that TWO CTAs per SM overlap each other's load / MMA / softmax latencies.
 // ------------------------------------------------------------------------------------------------
 struct AttnTcParams {
   __nv_bfloat16* out;
@@ -211,16 +213,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-constexpr int kAttnTcThreads = 160;
+constexpr int kAttnTcThreads = 288;      // warp 0: TMA + MMA issue; warps 1-8: softmax / epilogue, two per TMEM lane quadrant
+__host__ __device__ inline size_t attn_tc_kv_bytes(int kv_box_rows, int kv_boxes) {
+  return (static_cast<size_t>(kv_box_rows) * kv_boxes * 128 + 1023) / 1024 * 1024;
+}
+// shared memory: V | [ Q tile | K ] -- the P blocks (128 rows x 64 keys each) overlay Q and K, which are dead once S sits in TMEM
+__host__ __device__ inline size_t attn_tc_p_bytes(int spad, int kv_box_rows, int kv_boxes) {
+  const size_t p = static_cast<size_t>((spad + 63) / 64) * 16384;
+  const size_t qk = 16384 + attn_tc_kv_bytes(kv_box_rows, kv_boxes);
+  return p > qk ? p : qk;
+}
 __host__ __device__ inline size_t attn_tc_smem_bytes(int spad, int kv_box_rows, int kv_boxes) {
-  const size_t kv = static_cast<size_t>(kv_box_rows) * kv_boxes * 128;
-  const size_t pblk = static_cast<size_t>((spad + 63) / 64) * 16384;
-  return 1024 + 2 * ((kv + 1023) / 1024 * 1024) + pblk + 128;
+  return 1024 + attn_tc_kv_bytes(kv_box_rows, kv_boxes) + attn_tc_p_bytes(spad, kv_box_rows, kv_boxes) + 64 + 1024;
 }
 
 // bounded wait: a protocol bug must show up as wrong numbers in a test, never as a hung device
 __device__ __forceinline__ void mbar_wait_lim(uint64_t* bar, uint32_t parity) {
-  for (unsigned int i = 0; i < (1u << 26); ++i)
+  for (unsigned int i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return;
 }
 
@@ -229,19 +238,19 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t attn_tc_raw[];
   uint8_t* smem = attn_tc_raw + ((1024u - (smem_u32(attn_tc_raw) & 1023u)) & 1023u);
-  const size_t kv_bytes = (static_cast<size_t>(p.kv_box_rows) * p.kv_boxes * 128 + 1023) / 1024 * 1024;
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + kv_bytes;
-  uint8_t* sP = smem + 2 * kv_bytes;                 // k-blocks of [128 rows x 64 keys]; block 0 doubles as the Q tile
-  const int n_pblk = (p.spad + 63) / 64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + static_cast<size_t>(n_pblk) * 16384);
-  uint64_t* bar_kv = bars;       // K and V landed
-  uint64_t* bar_q = bars + 1;    // Q tile landed
+  const size_t kv_bytes = attn_tc_kv_bytes(p.kv_box_rows, p.kv_boxes);
+  uint8_t* sV = smem;
+  uint8_t* sP = smem + kv_bytes;                     // P blocks; block 0 doubles as the Q tile ...
+  uint8_t* sK = sP + 16384;                          // ... and K (re-fetched per query tile, an L2 hit) sits in blocks 1..
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + attn_tc_p_bytes(p.spad, p.kv_box_rows, p.kv_boxes));
+  uint64_t* bar_v = bars;        // V landed (once)
+  uint64_t* bar_q = bars + 1;    // Q tile + K landed
   uint64_t* bar_s = bars + 2;    // S complete in TMEM
-  uint64_t* bar_p = bars + 3;    // P written (4 warps)
+  uint64_t* bar_p = bars + 3;    // P written (8 warps)
   uint64_t* bar_o = bars + 4;    // O complete in TMEM
-  uint64_t* bar_free = bars + 5; // the softmax warps are done with O (4 warps): TMEM and the Q / P region may be reused
+  uint64_t* bar_free = bars + 5; // the softmax warps are done with O (8 warps): TMEM and the Q / K / P region may be reused
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* row_sums = reinterpret_cast<float*>(bars + 8);     // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -252,12 +261,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(bar_kv, 1);
+    mbar_init(bar_v, 1);
     mbar_init(bar_q, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
+    mbar_init(bar_p, 8);
     mbar_init(bar_o, 1);
-    mbar_init(bar_free, 4);
+    mbar_init(bar_free, 8);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -271,20 +280,20 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      // K and V of this (batch, head): once
-      mbar_arrive_expect_tx(bar_kv, static_cast<uint32_t>(2 * p.kv_boxes * p.kv_box_rows * 128));
-      for (int i = 0; i < p.kv_boxes; ++i) {
-        const int row = static_cast<int>(b * p.kv_rows_per_batch) + i * p.kv_box_rows;
-        tma_load_2d(sK + static_cast<size_t>(i) * p.kv_box_rows * 128, &tmK, bar_kv, p.k_col0 + h * 64, row);
-        tma_load_2d(sV + static_cast<size_t>(i) * p.kv_box_rows * 128, &tmV, bar_kv, p.v_col0 + h * 64, row);
-      }
+      const uint32_t kbytes = static_cast<uint32_t>(p.kv_boxes * p.kv_box_rows * 128);
+      mbar_arrive_expect_tx(bar_v, kbytes);
+      for (int i = 0; i < p.kv_boxes; ++i)
+        tma_load_2d(sV + static_cast<size_t>(i) * p.kv_box_rows * 128, &tmV, bar_v, p.v_col0 + h * 64,
+                    static_cast<int>(b * p.kv_rows_per_batch) + i * p.kv_box_rows);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);     // B operand (V) is MN-major
       for (int tile = 0; tile < n_tiles; ++tile) {
         const uint32_t ph = tile & 1;
         if (tile > 0) { mbar_wait_lim(bar_free, ph ^ 1); tc_fence_after(); }
-        mbar_arrive_expect_tx(bar_q, 128 * 128);
+        mbar_arrive_expect_tx(bar_q, 128 * 128 + kbytes);
         tma_load_2d(sP, &tmQ, bar_q, p.q_col0 + h * 64, static_cast<int>(b * p.q_rows_per_batch) + tile * 128);
-        if (tile == 0) mbar_wait_lim(bar_kv, 0);
+        for (int i = 0; i < p.kv_boxes; ++i)
+          tma_load_2d(sK + static_cast<size_t>(i) * p.kv_box_rows * 128, &tmK, bar_q, p.k_col0 + h * 64,
+                      static_cast<int>(b * p.kv_rows_per_batch) + i * p.kv_box_rows);
         mbar_wait_lim(bar_q, ph);
         tc_fence_after();
         // S = Q K^T: N in pieces of <= 256 key columns, K = 64 head dims = 4 MMAs each
@@ -298,6 +307,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         umma_commit(bar_s);
         // O = P V once the softmax warps have written P
+        if (tile == 0) mbar_wait_lim(bar_v, 0);
         mbar_wait_lim(bar_p, ph);
         tc_fence_after();
         const int nk16 = p.spad / 16;
@@ -308,8 +318,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else {
-    // ---- softmax / epilogue: thread = query row = TMEM lane ----
+    // ---- softmax / epilogue: thread = query row = TMEM lane; the two warps of a quadrant split the key columns ----
     const int quad = warp & 3;
+    const int half = (warp - 1) >> 2;
     const int row = quad * 32 + lane;                 // row of the tile
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int n16 = p.spad / 16;
@@ -317,18 +328,29 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t ph = tile & 1;
       mbar_wait_lim(bar_s, ph);
       tc_fence_after();
+      // pass 1: the row maximum (both warps over all columns: TMEM reads are cheap, a cross-warp exchange is not)
       float mx = -INFINITY;
-      for (int c = 0; c < n16; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_lane + c * 16, r);
-        tmem_ld_wait();
+      for (int c0 = 0; c0 < p.spad; c0 += 32) {
+        if (c0 + 32 <= p.spad) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + c0, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c * 16 + j < p.S) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.S) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_lane + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.S) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
       }
+      // pass 2: this warp's 16-column chunks -> P (bf16, K-major swizzled operand layout), partial row sum
       float sum = 0.f;
       const float mb = mx * p.scale_log2;
-      for (int c = 0; c < n16; ++c) {
+      for (int c = half; c < n16; c += 2) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_lane + c * 16, r);
         tmem_ld_wait();
@@ -345,18 +367,21 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         *reinterpret_cast<uint4*>(blk + (((ch) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(blk + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+      row_sums[half * 128 + row] = sum;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
-      // ---- O / row sum -> bf16 row ----
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the partner warp's partial row sum
+      const float inv = 1.0f / (row_sums[row] + row_sums[128 + row]);
+      // ---- O / row sum -> bf16 row (each warp: two of the four 16-column chunks) ----
       mbar_wait_lim(bar_o, ph);
       tc_fence_after();
-      const float inv = 1.0f / sum;
       const int qrow = tile * 128 + row;
       __nv_bfloat16* orow = p.out + b * p.o_bs + static_cast<long long>(qrow) * p.o_rs + h * 64;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * cc + half;
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_lane + c * 16, r);
         tmem_ld_wait();
@@ -375,7 +400,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       tc_fence_before();
-      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // row_sums are rewritten by the next tile
       if (lane == 0) mbar_arrive(bar_free);
     }
   }

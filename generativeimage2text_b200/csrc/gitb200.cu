@@ -1279,13 +1279,14 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
 // up to 512 rows are staged per round as 1-2 TMA boxes of <= 256 rows.
 static int set_attn_smem_limit(gitb200_engine* h) {
   const int M = h->cur_M;
-  const int chunk = M <= 384 ? M : 256;   // two (K + V) buffers of `chunk` rows must fit in shared memory
-  const int nb = (chunk + 255) / 256;
-  h->attn_box_rows = (chunk + nb - 1) / nb;
-  h->attn_chunk_rows = h->attn_box_rows * nb;
-  // two buffers (K + V each) per CTA; two CTAs per SM when they fit next to each other
+  // chunks of at most 224 keys: two (K + V) staging buffers of one chunk per CTA, and at least two CTAs per SM (M = 257
+  // in one piece was 131 KB per CTA = one 4-warp CTA per SM: 44 us per launch at 128 beam rows, profiles/launches_r02_config3.csv)
+  const int n_chunks = (M + 223) / 224;
+  h->attn_box_rows = (M + n_chunks - 1) / n_chunks;
+  h->attn_chunk_rows = h->attn_box_rows;
   h->attn_smem = static_cast<size_t>(4) * h->attn_chunk_rows * 128 + 128;
-  const int per_sm = (h->attn_smem * 2 + 8 * 1024 <= 227 * 1024) ? 2 : 1;
+  int per_sm = static_cast<int>((227 * 1024) / (h->attn_smem + 8 * 1024));
+  per_sm = std::max(1, std::min(per_sm, 4));
   const int items = h->cur_B * h->cfg.dec_heads;
   h->attn_grid = std::min(items, per_sm * h->num_sms);
   CK(cudaFuncSetAttribute(decode_attn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));

@@ -68,74 +68,101 @@ __device__ __forceinline__ float beam_length_norm(int length, float lp) {
   return powf(5.0f + static_cast<float>(length), lp) / powf(6.0f, lp);
 }
 
-// One CTA per row: lse = logsumexp(z), then the row's top-NC values of (z - lse + beam_score[row]).
+// Sorted candidate list of kMaxCand entries in registers (descending value, ascending index on exact ties).  Every access is
+// statically indexed: the round-1 version indexed the arrays with a runtime position, which put them in local memory and
+// made this kernel 144 us per step at 128 rows (profiles/launches_r02_config3.csv).
+struct TopList {
+  float v[kMaxCand];
+  int i[kMaxCand];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < kMaxCand; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
+  }
+  static __device__ __forceinline__ bool before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+  __device__ __forceinline__ void push(float val, int idx) {          // insert if it beats the last entry, keep sorted
+    if (!before(val, idx, v[kMaxCand - 1], i[kMaxCand - 1])) return;
+    v[kMaxCand - 1] = val; i[kMaxCand - 1] = idx;
+#pragma unroll
+    for (int k = kMaxCand - 1; k > 0; --k) {
+      if (before(v[k], i[k], v[k - 1], i[k - 1])) {
+        const float tv = v[k]; v[k] = v[k - 1]; v[k - 1] = tv;
+        const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
+      }
+    }
+  }
+};
+
+// One CTA per row: lse = logsumexp(z), then the row's top-NC values of (z - lse + beam_score[row]).  One pass over the
+// logits (online max / sum-exp and a sorted top-8 list per thread), then lists merged by shuffles and through shared memory.
 __global__ void __launch_bounds__(256) beam_row_topk_kernel(const BeamParams p) {
   griddep_launch();
   griddep_wait();
   StepState* st = p.state;
   if (st->finished) return;
   const int row = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NC = p.per_node * p.beam;
   const float* z = p.logits + static_cast<long long>(row) * p.V;
   if (p.step_logits != nullptr) {
     float* dst = p.step_logits + (static_cast<long long>(st->step) * gridDim.x + row) * p.V;
     for (int i = tid; i < p.V; i += blockDim.x) dst[i] = z[i];
   }
-  __shared__ float s_red[256];
-  __shared__ float s_cv[256 * kMaxCand];
-  __shared__ int s_ci[256 * kMaxCand];
-  // thread-local sorted top-NC (descending value, ascending index on ties) + max
-  float tv[kMaxCand];
-  int ti[kMaxCand];
+  TopList top;
+  top.init();
+  float mx = -INFINITY, sum = 0.f;
+  for (int i0 = tid; i0 < p.V; i0 += 8 * 256) {       // 8 independent loads in flight per thread
+    float v[8];
 #pragma unroll
-  for (int k = 0; k < kMaxCand; ++k) { tv[k] = -INFINITY; ti[k] = 0x7fffffff; }
-  float mx = -INFINITY;
-  for (int i = tid; i < p.V; i += blockDim.x) {
-    const float v = z[i];
-    mx = fmaxf(mx, v);
-    if (v > tv[NC - 1]) {
-      int k = NC - 1;
-      while (k > 0 && v > tv[k - 1]) { tv[k] = tv[k - 1]; ti[k] = ti[k - 1]; --k; }
-      tv[k] = v; ti[k] = i;
+    for (int u = 0; u < 8; ++u) v[u] = (i0 + u * 256 < p.V) ? __ldcg(z + i0 + u * 256) : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (v[u] == -INFINITY) continue;
+      if (v[u] > mx) { sum = sum * __expf(mx - v[u]) + 1.0f; mx = v[u]; } else { sum += __expf(v[u] - mx); }
+      top.push(v[u], i0 + u * 256);
     }
   }
-  s_red[tid] = mx;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) { if (tid < o) s_red[tid] = fmaxf(s_red[tid], s_red[tid + o]); __syncthreads(); }
-  mx = s_red[0];
-  __syncthreads();
-  float sum = 0.f;
-  for (int i = tid; i < p.V; i += blockDim.x) sum += __expf(z[i] - mx);
-  s_red[tid] = sum;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
-  const float log_sum = logf(s_red[0]);
-  for (int k = 0; k < NC; ++k) { s_cv[tid * kMaxCand + k] = tv[k]; s_ci[tid * kMaxCand + k] = ti[k]; }
-  __syncthreads();
-  // tree merge of the 256 sorted lists
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) {
-      float av[kMaxCand], bv[kMaxCand];
-      int ai[kMaxCand], bi[kMaxCand];
-      for (int k = 0; k < NC; ++k) {
-        av[k] = s_cv[tid * kMaxCand + k]; ai[k] = s_ci[tid * kMaxCand + k];
-        bv[k] = s_cv[(tid + o) * kMaxCand + k]; bi[k] = s_ci[(tid + o) * kMaxCand + k];
-      }
-      int ia = 0, ib = 0;
-      for (int k = 0; k < NC; ++k) {
-        const bool take_a = (av[ia] > bv[ib]) || (av[ia] == bv[ib] && ai[ia] <= bi[ib]);
-        if (take_a) { s_cv[tid * kMaxCand + k] = av[ia]; s_ci[tid * kMaxCand + k] = ai[ia]; ++ia; }
-        else { s_cv[tid * kMaxCand + k] = bv[ib]; s_ci[tid * kMaxCand + k] = bi[ib]; ++ib; }
-      }
-    }
-    __syncthreads();
+  // warp-level merge: each round a lane absorbs its partner's list (entries arrive in sorted order: push keeps ours sorted)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, mx, o);
+    const float s_o = __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mn = fmaxf(mx, m_o);
+    sum = sum * ((mx == -INFINITY) ? 0.f : __expf(mx - mn)) + s_o * ((m_o == -INFINITY) ? 0.f : __expf(m_o - mn));
+    mx = mn;
+    float pv[kMaxCand];
+    int pi[kMaxCand];
+#pragma unroll
+    for (int k = 0; k < kMaxCand; ++k) { pv[k] = __shfl_xor_sync(0xffffffffu, top.v[k], o); pi[k] = __shfl_xor_sync(0xffffffffu, top.i[k], o); }
+#pragma unroll
+    for (int k = 0; k < kMaxCand; ++k) top.push(pv[k], pi[k]);
   }
-  if (tid < NC) {
+  __shared__ float s_m[8], s_s[8];
+  __shared__ float s_cv[8][kMaxCand];
+  __shared__ int s_ci[8][kMaxCand];
+  if (lane == 0) {
+    s_m[warp] = mx; s_s[warp] = sum;
+#pragma unroll
+    for (int k = 0; k < kMaxCand; ++k) { s_cv[warp][k] = top.v[k]; s_ci[warp][k] = top.i[k]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) {
+      const float mn = fmaxf(mx, s_m[w]);
+      sum = sum * ((mx == -INFINITY) ? 0.f : __expf(mx - mn)) + s_s[w] * ((s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - mn));
+      mx = mn;
+#pragma unroll
+      for (int k = 0; k < kMaxCand; ++k) top.push(s_cv[w][k], s_ci[w][k]);
+    }
+    const float log_sum = logf(sum);
     const float bs = p.s.beam_scores[row];
-    // log_softmax (x - max - log(sum exp(x - max))) + beam score (reference :1169-1172)
-    p.s.cand_val[row * kMaxCand + tid] = ((s_cv[tid] - mx) - log_sum) + bs;
-    p.s.cand_idx[row * kMaxCand + tid] = s_ci[tid];
+#pragma unroll
+    for (int k = 0; k < kMaxCand; ++k) {
+      if (k < NC) {
+        // log_softmax (x - max - log(sum exp(x - max))) + beam score (reference :1169-1172)
+        p.s.cand_val[row * kMaxCand + k] = ((top.v[k] - mx) - log_sum) + bs;
+        p.s.cand_idx[row * kMaxCand + k] = top.i[k];
+      }
+    }
   }
 }
 
