@@ -74,12 +74,12 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (per launch) from the committed
-    `ncu --set full` capture (profiles/prof_gemm_r01.md): 24.1 MB read + 24.8 MB write."""
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` captures
+    (profiles/roofline_traffic.json names the .ncu-rep extract each figure comes from)."""
     p = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(p):
-        return json.load(open(p)).get('dram_bytes_per_launch')
+        return json.load(open(p)).get(kernel, {}).get('dram_bytes_per_launch')
     return None
 
 
@@ -393,7 +393,28 @@ def main():
     peaks = measured_peaks()
     lib = _lib.load()
     roofline = None
+    roofline_gemm = None
     work = algorithmic_work(cfg)
+    if rank == 0 and cfg['search'] == 'greedy':
+        # dominant kernel of a greedy call = decode_mega_kernel, one launch per decode step (profiles/launches_r02_*: ~2/3 of
+        # a config-2 call).  HBM bound: algorithmic bytes per launch = the bf16 decoder weights + LM head, the image K/V of
+        # every sequence and the text K/V so far (SURVEY.md 8d 'step bytes', averaged over the call's steps); duration =
+        # CUDA events on the engine's stream around the call's decode loop / its step launches (gitb200_last_decode_ms).
+        with torch.cuda.stream(stream):
+            one_step(dev_batches, False, 1, 1)          # no collective here: this leg runs on rank 0 only
+            ms_loop, n_launch, one_kernel = model.last_decode_timing()
+        if one_kernel:
+            bytes_per_launch = work['decode_bytes'] / (MAX_STEPS - 1)
+            avg_ms = ms_loop / n_launch
+            achieved = bytes_per_launch / (avg_ms / 1e3) / 1e9
+            roofline = {'kernel': 'decode_mega_kernel (one persistent 148-CTA launch per decode step: 6 decoder layers + LM head + '
+                                  'argmax / log-softmax + next embedding for %d sequences)' % B,
+                        'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                        'frac': achieved / peaks['hbm_gbs'], 'traffic': ncu_traffic('decode_mega_kernel') if args.config == 2 else None,
+                        'avg_launch_ms': avg_ms, 'launches_timed': n_launch,
+                        'algorithmic_bytes_per_launch': bytes_per_launch,
+                        'peak_source': peaks['source'] + ', HBM copy bandwidth; the launches run back to back inside a call, '
+                                       'so the figure includes the ~2 us between two graph launches'}
     if rank == 0 and not args.no_micro:
         # dominant kernel = the tcgen05 GEMM family (profiles/: > 1/2 of a call); its largest instance is the ViT MLP c_fc
         # GEMM [images * L, d] x [d, 4d] (+bias +QuickGELU, bf16 out): algorithmic FLOPs = 2*M*N*K.
@@ -423,9 +444,9 @@ def main():
         avg_ms = sum(durs) / len(durs)
         flops = 2.0 * M * N * K
         achieved = flops / (avg_ms / 1e3) / 1e12
-        roofline = {'kernel': 'gemm2_bf16_tcgen05<256> (ViT mlp.c_fc shape %dx%dx%d, bias+QuickGELU epilogue)' % (M, N, K),
+        roofline_gemm = {'kernel': 'gemm2_bf16_tcgen05<256> (ViT mlp.c_fc shape %dx%dx%d, bias+QuickGELU epilogue)' % (M, N, K),
                     'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                    'frac': achieved / peaks['bf16_tflops'], 'traffic': ncu_traffic() if args.config == 2 else None,
+                    'frac': achieved / peaks['bf16_tflops'], 'traffic': ncu_traffic('gemm2_bf16_tcgen05') if args.config == 2 else None,
                     'avg_launch_ms': avg_ms,
                     'peak_source': peaks['source'] + ', burst bf16 figure (kernel timed alone, L2 flushed between launches)'}
     # whole-call roofline: tensor part at the sustained GEMM peak + decode bytes at the HBM peak
@@ -464,7 +485,8 @@ def main():
                     'api': "model({'image': pinned host tensor(s)}) -> predictions.cpu(), logprobs.cpu()"},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
-            'roofline': roofline,
+            'roofline': roofline if roofline is not None else roofline_gemm,
+            'roofline_encoder_gemm': roofline_gemm if roofline is not None else None,
             'whole_call': whole,
             'serving': serving,
             'cpu_baseline': cpu,

@@ -54,6 +54,7 @@ SIGNATURES = {
     'gitb200_generate_host_async': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.POINTER(Search),
                                             c_void_p, c_void_p, c_void_p]),
     'gitb200_generate_finish': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_int32)]),
+    'gitb200_last_decode_ms': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     'gitb200_set_row_prefixes': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'gitb200_launch_count': (c_int64, [c_void_p]),
     'gitb200_set_option': (c_int, [c_void_p, c_char_p, c_int64]),

@@ -4,19 +4,27 @@
 // gitb200.cu::step_layers for that case.
 //
 // Why: at <= 64 rows every kernel of the chain is latency bound (TMA -> tcgen05 -> TMEM -> epilogue -> flag, ~7 us per
-// hop, 341 us per step against an HBM floor of 59 us).  Here the HBM stream is decoupled from the dependency chain:
+// hop, ~400 us per step against an HBM floor of ~50 us).  Here the HBM stream is decoupled from the dependency chain:
 //   * 148 CTAs (one per SM, cooperative launch), 8 compute warps + 1 producer warp each;
-//   * every byte the step reads from HBM that does NOT depend on the step -- the weight slice a CTA owns in each GEMM
-//     phase and the image K/V slices of its attention items -- flows through a 12 x 16 KB shared-memory ring that the
-//     producer warp fills in program order with TMA (bulk copies of pre-packed weight tiles, 128-row swizzled boxes of
-//     the K/V cache), running as far ahead of the compute warps as the ring allows, across phase boundaries;
+//   * every byte the step reads from HBM -- the weight tiles a CTA owns in each GEMM phase, the image K/V of its attention
+//     items and the text K/V so far -- flows through a 12 x 16 KB shared-memory ring that the producer warp fills in
+//     program order with TMA (bulk copies of pre-packed weight tiles, 64-key swizzled K | V box pairs), running as far
+//     ahead of the compute warps as the ring allows, across phase boundaries (only the text K/V of the CURRENT layer waits
+//     for that layer's QKV phase);
 //   * phases (QKV | attention | out-proj | LN | fc1 | fc2 | LN per layer, then LM head | selection + embedding) are
-//     separated by a grid barrier (one release-add + acquire-spin on a global counter); what crosses a barrier is only
-//     the <= 64-row activations, read straight from L2 into mma.sync fragments;
-//   * weights are stationary per CTA: a GEMM phase gives CTA c the output features [f0, f0 + n) over the FULL reduction
-//     (no split-K, no partial buffers, bit-reproducible); the 8 warps split it 4 row tiles x 2 K halves.
+//     separated by a grid barrier (one release-add + acquire-spin on a global counter, 1.7 us on B200 -- the cheapest of
+//     the variants tools/barrier_bench.cu times); what crosses a barrier is only the <= 64-row activations, read straight
+//     from L2 into mma.sync fragments;
+//   * weights are stationary per CTA: a GEMM phase gives CTA c a few 8-feature tiles over a 768-long reduction; the 8 warps
+//     split a tile 4 row tiles x 2 K halves.  fc2 (K = 3072) is dealt as 4 k slices x 96 feature tiles over 128 CTAs, its
+//     four partial sums meet in slice order in the LayerNorm phase: no atomics anywhere, the step is bit-reproducible;
+//   * attention: `att_split` warps per (sequence, head) item, 64 keys per ring slot, online softmax, fixed-order merge.
 // The skinny GEMMs and the 1-row attention are HBM-bound byte work (arithmetic intensity ~rows FLOP/B): they use the
-// warp-level mma.sync path fed from shared memory; tcgen05 / TMEM stay with the compute-bound encoder and prefill GEMMs.
+// warp-level mma.sync path fed from shared memory (measured limit here: ~0.77 us per 64 x 8 x 768 tile per SM, which is
+// what the 26-tile LM-head slice of a CTA costs); tcgen05 / TMEM stay with the compute-bound encoder and prefill GEMMs:
+// with the weights as the M operand a tcgen05 tile needs >= 64 weight rows per CTA (3/4 of the SMs, and of the HBM stream,
+// would idle in the layer GEMMs); with the activations as the M operand every CTA would have to stage the 64 x 768
+// activations (96 KB) in shared memory in every phase, which the 192 KB ring leaves no room for.
 #pragma once
 #include "ptx.cuh"
 #include "rowops.cuh"
@@ -37,7 +45,7 @@ struct MegaLayer {
   const uint8_t* wqkv;     // [288] tiles: features 8t .. 8t+7 of the fused q | k | v projection
   const uint8_t* wo;       // [96]
   const uint8_t* w1;       // [384]
-  const uint8_t* w2;       // [96][4]: feature tile x 768-wide k slice
+  const uint8_t* w2;       // [96][4]: feature tile x 768-wide k slice (CTA c < 128: slice c & 3 of tiles 3 (c >> 2) .. + 2)
   const float* bqkv; const float* bo; const float* b1; const float* b2;
   const float* lnag; const float* lnab; const float* lnog; const float* lnob;
   __nv_bfloat16* txt_k;    // [R, T_alloc, 768]
@@ -52,6 +60,7 @@ struct MegaParams {
   const float* positions;  // fp32 [max_pos, 768]
   const float* lnemb_g; const float* lnemb_b;
   int R, M, T_alloc, V, n_layers;
+  int att_split;           // warps per attention item (1, 2, 4 or 8; host: as many as the CTA's item count leaves room for)
   // activations (global, L2 resident)
   float* x;                // [R, 768] residual stream (post-LayerNorm)
   float* y;                // [R, 768] pre-LayerNorm sum (after the attention block)
@@ -305,9 +314,10 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         const MegaLayer& L = p.layer[l];
         if (cta < 144) for (int j = 0; j < 2; ++j) tile(L.wqkv + static_cast<size_t>(cta * 2 + j) * kMegaTileBytes);
         // attention chunks of this CTA's items, ROUND-ROBIN over the items (each item is walked by its own warp, see the
-        // consumer): round r = image keys 64r .. 64r + 63 of every item, then the text rounds.  Eight items at a time.
-        for (int k0 = 0; k0 < n_my_items; k0 += kMegaComputeWarps) {
-          const int kn = min(kMegaComputeWarps, n_my_items - k0);
+        // consumer): round r = image keys 64r .. 64r + 63 of every item, then the text rounds, `att_slots` items at a time.
+        const int att_slots = kMegaComputeWarps / p.att_split;      // items walked concurrently (see the consumer)
+        for (int k0 = 0; k0 < n_my_items; k0 += att_slots) {
+          const int kn = min(att_slots, n_my_items - k0);
           for (int r = 0; r < n_kv + n_txt; ++r) {
             if (r == n_kv) {
               // the text K/V of position `pos` exist once every CTA has passed barrier 7l + 1 (after this layer's QKV phase)
@@ -333,7 +343,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         }
         if (cta < 96) tile(L.wo + static_cast<size_t>(cta) * kMegaTileBytes);
         if (cta < 128) for (int j = 0; j < 3; ++j) tile(L.w1 + static_cast<size_t>(cta * 3 + j) * kMegaTileBytes);
-        if (cta < 96) for (int j = 0; j < 4; ++j) tile(L.w2 + static_cast<size_t>(((cta >> 2) * 4 + j) * 4 + (cta & 3)) * kMegaTileBytes);
+        if (cta < 128) for (int j = 0; j < 3; ++j) tile(L.w2 + static_cast<size_t>(((cta >> 2) * 3 + j) * 4 + (cta & 3)) * kMegaTileBytes);
       }
       for (int j = 0; j < lm_n; ++j) tile(p.lm + static_cast<size_t>(lm_t0 + j) * kMegaTileBytes);
     }
@@ -386,15 +396,21 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     }
     mega_grid_sync(bar, epoch, p.error);
     // ------------------------------------------------ P2: attention ------------------------------------------------
-    // One WARP per (sequence, head) item: no block-level synchronisation and no cross-warp merge inside the phase.  The
-    // item's image K/V chunks and its text K/V box arrive through the ring; S = q K^T and O += P V run on mma.sync with a
-    // 16-row q tile whose row 0 is the query (rows 1..15 zero), 64 keys at a time with an online softmax.
+    // `att_split` warps per (sequence, head) item (1 when the CTA has 5-8 items, up to 8 for small or long-sequence batches):
+    // the item's 64-key chunks -- image K/V and text K/V, all through the ring -- are dealt to its warps round by round;
+    // S = q K^T and O += P V run on mma.sync with a 16-row q tile whose row 0 is the query (rows 1..15 zero) and an online
+    // softmax per 64 keys; the warps of an item merge their softmax states through shared memory.  No block-wide barrier.
     {
       const int rounds = n_kv + n_txt;                      // ring chunks per item (64 keys each), dealt round-robin
       const uint32_t att_base = rg.idx;
       uint8_t* qw = q_s + warp * 2048;
       constexpr float kLog2e = 1.44269504088896340736f;
-      for (int k = warp; k < n_my_items; k += kMegaComputeWarps) {
+      const int W = p.att_split, att_slots = kMegaComputeWarps / W;
+      const int slot = warp / W, part = warp - slot * W;
+      for (int k0 = 0; k0 < n_my_items; k0 += att_slots) {
+        const int kn = min(att_slots, n_my_items - k0);
+        if (slot >= kn) continue;
+        const int k = k0 + slot;
         const int item = my_cta_rev + k * G;
         const int b = item / kMegaH, h = item - b * kMegaH;
         // q tile (already scaled by 1/8), 128B-swizzled like the K/V boxes: lanes 0..7 fetch row 0, everything else is zero
@@ -471,10 +487,9 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
             }
           }
         };
-        // chunk (item k, round r) sits at  att_base + [items before this group of eight] * rounds + r * kn + (k % 8)
-        const int k0 = k - warp, kn = min(kMegaComputeWarps, n_my_items - k0);
-        const uint32_t c0 = att_base + static_cast<uint32_t>(k0) * rounds + warp;
-        for (int r = 0; r < rounds; ++r) {
+        // chunk (item k, round r) sits at  att_base + [items of earlier groups] * rounds + r * kn + slot
+        const uint32_t c0 = att_base + static_cast<uint32_t>(k0) * rounds + slot;
+        for (int r = part; r < rounds; r += W) {
           const uint32_t ci = c0 + static_cast<uint32_t>(r) * kn;
           const uint32_t sK = smem_u32(rg.acquire_at(ci));
           if (r < n_kv) keys64(sK, sK + 8192, 0, r * kMegaKvRows, M);               // image keys 64r ..
@@ -483,11 +498,37 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         }
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-        if (g == 0) {
-          const float inv = 1.0f / l_run;
-          __nv_bfloat16* dst = p.ctx + static_cast<long long>(b) * kMegaD + h * 64 + 2 * t;
+        if (W == 1) {
+          if (g == 0) {
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = p.ctx + static_cast<long long>(b) * kMegaD + h * 64 + 2 * t;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16(o[j][0] * inv, o[j][1] * inv);
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16(o[j][0] * inv, o[j][1] * inv);
+          }
+        } else {
+          // merge the W softmax states of this item (fixed order: bit-reproducible)
+          float* pp = att_part + warp * 68;
+          if (g == 0) {
+            if (t == 0) { pp[64] = m_run; pp[65] = l_run; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { pp[8 * j + 2 * t] = o[j][0]; pp[8 * j + 2 * t + 1] = o[j][1]; }
+          }
+          named_bar_sync(6 + slot, W * 32);
+          if (part == 0) {
+            const float* p0 = att_part + (slot * W) * 68;
+            float mm = -INFINITY;
+            for (int i = 0; i < W; ++i) mm = fmaxf(mm, p0[i * 68 + 64]);
+            float lsum = 0.f, a0 = 0.f, a1 = 0.f;
+            for (int i = 0; i < W; ++i) {
+              const float mi = p0[i * 68 + 64];
+              const float wgt = (mi == -INFINITY) ? 0.f : exp2f((mi - mm) * kLog2e);
+              lsum += p0[i * 68 + 65] * wgt;
+              a0 += p0[i * 68 + 2 * lane] * wgt;
+              a1 += p0[i * 68 + 2 * lane + 1] * wgt;
+            }
+            *reinterpret_cast<uint32_t*>(p.ctx + static_cast<long long>(b) * kMegaD + h * 64 + 2 * lane) = pack_bf16(a0 / lsum, a1 / lsum);
+          }
+          named_bar_sync(6 + slot, W * 32);                 // the partial states are rewritten by the item's next group
         }
         __syncwarp();                                       // the q tile is rewritten by this warp's next item
       }
@@ -607,22 +648,22 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       }
     }
     mega_grid_sync(bar, epoch, p.error);
-    // ------------------------------------------------ P6: fc2, split over CTAs: 24 groups of 32 features x 4 k slices ------
+    // ------------------------------------------------ P6: fc2, split over CTAs: 32 groups of 24 features x 4 k slices ------
     // (each CTA reads ONE 768-wide slice of the activations; the four partial sums of a feature meet, in slice order, in
     //  the LayerNorm phase below -- bit-reproducible, no atomics)
-    if (cta < 96) {
+    if (cta < 128) {
       const int ks = cta & 3, fg = cta >> 2;
       MegaAFrag a;
       mega_load_a(a, p.ub + ks * kMegaD, kMegaF, R, mt, kh, lane);
       float* yp = p.ypart + static_cast<long long>(ks) * R * kMegaD;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 3; ++j) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
         const uint8_t* tb = rg.acquire();
         mega_mma_tile(c, a, tb, kh, lane);
         rg.release();
         if (mega_combine(c, red, red_buf, mt, kh, lane)) {
-          const int f = (fg * 4 + j) * 8 + 2 * t;
+          const int f = (fg * 3 + j) * 8 + 2 * t;
           if (r0 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r0) * kMegaD + f) = make_float2(c[0], c[1]);
           if (r1 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r1) * kMegaD + f) = make_float2(c[2], c[3]);
         }

@@ -173,6 +173,9 @@ struct gitb200_engine {
   bool pend_beam = false;
   cudaStream_t pend_stream = nullptr;
   cudaEvent_t chunk_ev[2] = {nullptr, nullptr};   // decode-loop chunks (generate_impl)
+  cudaEvent_t dec_ev[2] = {nullptr, nullptr};     // around the decode loop of the last generate (gitb200_last_decode_ms)
+  int dec_steps = 0;                               // step launches between them
+  bool dec_mega = false;                           // ... each of which was one decode_mega_kernel launch
   // per-row prefixes of the NEXT generate call (gitb200_set_row_prefixes; consumed by that call)
   const int64_t* rp_tok = nullptr;
   const int32_t* rp_lens = nullptr;
@@ -759,6 +762,7 @@ extern "C" void gitb200_destroy(gitb200_engine* h) {
   if (h->host_state) cudaFreeHost(h->host_state);
   if (h->own_event) cudaEventDestroy(h->own_event);
   for (int i = 0; i < 2; ++i) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+  for (int i = 0; i < 2; ++i) if (h->dec_ev[i]) cudaEventDestroy(h->dec_ev[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   release_all(h);
   delete h;

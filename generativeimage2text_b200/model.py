@@ -317,6 +317,15 @@ class GitB200CaptioningModel(nn.Module):
                 lib, _ = self._ensure_engine(k)
                 _lib.check(lib.gitb200_set_option(self._slots[k]['engine'], name.encode(), int(value)), self._slots[k]['engine'], 'set_option')
 
+    def last_decode_timing(self):
+        """(device ms of the last call's decode loop, step launches in it, whether each was one decode_mega_kernel
+        launch) -- CUDA events on the engine's stream (include/gitb200.h gitb200_last_decode_ms); bench.py's roofline."""
+        lib = _lib.load()
+        ms, steps, one = ctypes.c_float(), ctypes.c_int32(), ctypes.c_int32()
+        h = self._slots[0]['engine']
+        _lib.check(lib.gitb200_last_decode_ms(h, ctypes.byref(ms), ctypes.byref(steps), ctypes.byref(one)), h, 'last_decode_ms')
+        return ms.value, steps.value, bool(one.value)
+
     def launch_count(self):
         lib = _lib.load()
         return sum(int(lib.gitb200_launch_count(sl['engine'])) for sl in self._slots if sl['engine'] is not None)

@@ -141,6 +141,11 @@ int gitb200_generate_host_async(gitb200_engine* h, const float* images_host, int
                                 int64_t* tokens_out_host, float* logprobs_out_host, void* stream);
 int gitb200_generate_finish(gitb200_engine* h, int32_t* out_len_host);
 
+/* Measurement hook (bench.py's roofline): device time, by CUDA events on the engine's stream, of the decode loop of the
+ * last generate on this engine -- first step launch to last -- with the number of step launches in it and whether each
+ * was the single decode_mega_kernel launch.  Waits for that loop to finish.  No reference counterpart. */
+int gitb200_last_decode_ms(gitb200_engine* h, float* ms_out, int32_t* steps_out, int32_t* one_kernel_out);
+
 /* Per-row prefixes for the NEXT generate call (question batches; the reference allows one prefix and batch 1 only,
  * layers/decoder.py:985-1006): prefix_dev int64 [rows, stride], lens_dev int32 [rows] (1 <= len <= stride, len < max_steps;
  * tokens past a row's length are ignored).  rows must equal that call's batch; pass prefix_len = 0 to it.  Every row is
