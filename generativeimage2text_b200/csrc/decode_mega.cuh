@@ -103,6 +103,44 @@ __global__ void __launch_bounds__(256) pack_tiles_kernel(const __nv_bfloat16* __
 }
 
 // ---- small device helpers ------------------------------------------------------------------------------------------------
+// Fine-grained marks of the debug timeline build (tools/mega_timeline.py): thread 0 of CTA 0 stores (%clock64, id) pairs
+// into a slice of the timeline buffer reserved once per launch -- no atomics or %globaltimer reads inside the phases.
+#ifdef GITB200_TIMELINE
+struct MegaTl {
+  unsigned long long* buf;
+  unsigned int n;
+  __device__ __forceinline__ void begin() {
+    buf = nullptr; n = 0;
+    if (g_tl_buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      const unsigned int i = atomicAdd(&g_tl_count, 160u);
+      if (i + 160u <= kTimelineMax) {
+        buf = g_tl_buf + 2 * i;
+        for (int k = 0; k < 160; ++k) { buf[2 * k] = 0ull; buf[2 * k + 1] = 0ull; }
+        mark(700000); buf[2 * n] = globaltimer_ns(); buf[2 * n + 1] = 700001ull; ++n;
+      }
+    }
+  }
+  __device__ __forceinline__ void mark(int kid) {
+    if (buf != nullptr && n < 160u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+      buf[2 * n] = t; buf[2 * n + 1] = static_cast<unsigned long long>(kid); ++n;
+    }
+  }
+  __device__ __forceinline__ void end() {
+    if (buf != nullptr) { mark(700002); if (n < 160u) { buf[2 * n] = globaltimer_ns(); buf[2 * n + 1] = 700003ull; ++n; } }
+  }
+};
+#define MEGA_TL(kid) tlf.mark(kid)
+#else
+struct MegaTl {
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void end() {}
+};
+#define MEGA_TL(kid)
+#endif
+
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -132,6 +170,13 @@ struct MegaRing {
     if (!mbar_wait_bounded(&full[slot], (idx / kMegaSlots) & 1, error)) *error = 2;
     return base + slot * kMegaSlotBytes;
   }
+  // chunk idx + n (n < kMegaSlots) without consuming it: the GEMM phases take all tiles of a batch first, so that the MMAs
+  // of one tile overlap the shared-memory reads, the K-half exchange and the epilogue of its neighbours
+  __device__ __forceinline__ const uint8_t* acquire_ahead(uint32_t n) {
+    const uint32_t i = idx + n, slot = i % kMegaSlots;
+    if (!mbar_wait_bounded(&full[slot], (i / kMegaSlots) & 1, error)) *error = 2;
+    return base + slot * kMegaSlotBytes;
+  }
   __device__ __forceinline__ void release() {   // every compute warp, once per chunk
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[idx % kMegaSlots]);
@@ -158,13 +203,17 @@ struct MegaRing {
 };
 
 // Grid barrier between phases (compute warps only: 256 threads; the producer warp never waits for a phase).
-__device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned int& epoch, int* error) {
+__device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned int& epoch, int* error, MegaTl& tlf, int tl_id = 0) {
+  if (tl_id) tlf.mark(tl_id + 5);                                   // this warp's phase work issued
   named_bar_sync(1, kMegaComputeWarps * 32);
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
-    tl_mark_one(500000 + static_cast<int>(epoch / gridDim.x));      // this CTA arrived at barrier #n
+    if (tl_id) tlf.mark(tl_id + 6);                                 // all compute warps of the CTA are here
+    else tl_mark_one(500000 + static_cast<int>(epoch / gridDim.x)); // this CTA arrived at barrier #n
     __threadfence();
+    if (tl_id) tlf.mark(tl_id + 7);
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+    if (tl_id) tlf.mark(tl_id + 8);
     unsigned int spins = 0;
     while (ld_acquire_gpu(counter) < epoch) {
       if (++spins > kMegaSpinLimit || ((spins & 255u) == 255u && *reinterpret_cast<const volatile int*>(error) != 0)) {
@@ -172,9 +221,11 @@ __device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned i
         break;
       }
     }
-    tl_mark_one(600000 + static_cast<int>(epoch / gridDim.x));      // barrier #n released
+    if (tl_id) tlf.mark(tl_id + 9);
+    else tl_mark_one(600000 + static_cast<int>(epoch / gridDim.x)); // barrier #n released
   }
   named_bar_sync(1, kMegaComputeWarps * 32);
+  if (tl_id) tlf.mark(tl_id + 10);
 }
 
 // A operand of one GEMM phase: this warp's 16 rows x 384 k of a row-major bf16 activation matrix, straight from L2.
@@ -193,49 +244,70 @@ __device__ __forceinline__ void mega_load_a(MegaAFrag& a, const __nv_bfloat16* A
     a.hi[j] = (r1 < rows) ? __ldcg(p1 + 4 * j) : make_uint4(0, 0, 0, 0);
   }
 }
-// c += A(16 x 384 of this warp) * tile(8 features, this warp's k half).  Two independent accumulators (even / odd k-steps):
-// a single one would serialise 24 dependent MMAs (~0.4 us per tile, which made the 26-tile LM head latency bound); they
-// are added in a fixed order, so the result stays bit-reproducible.  (Four would spill: 9 warps cap the kernel at 168
-// registers per thread.)
-__device__ __forceinline__ void mega_mma_tile(float (&c)[4], const MegaAFrag& a, const uint8_t* tile, int kh, int lane) {
-  const uint2* bp = reinterpret_cast<const uint2*>(tile) + kh * 24 * 32 + lane;
-  float c1[4] = {0.f, 0.f, 0.f, 0.f};
+// c += A(16 x 384 of this warp) * tile(8 features, this warp's k half), NT tiles at once.  Per tile two independent
+// accumulators (even / odd k-steps, added in a fixed order: bit-reproducible) -- a single one would serialise 24 dependent
+// MMAs; across the NT tiles the 2 NT chains of a warp keep the tensor pipe busy over the MMA latency, and the NT tiles
+// share one K-half exchange.  (9 warps cap the kernel at 168 registers per thread: NT <= 3.)
+template <int NT>
+__device__ __forceinline__ void mega_mma_tiles(float (&c)[NT][4], const MegaAFrag& a, const uint8_t* const (&tile)[NT], int kh, int lane) {
+  const uint2* bp[NT];
+  float c1[NT][4];
 #pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    const uint2 b0 = bp[(2 * j) * 32];
-    const uint2 b1 = bp[(2 * j + 1) * 32];
-    const uint32_t a0[4] = {a.lo[j].x, a.hi[j].x, a.lo[j].y, a.hi[j].y};
-    const uint32_t a1[4] = {a.lo[j].z, a.hi[j].z, a.lo[j].w, a.hi[j].w};
-    mma_bf16_16816(c, a0, b0.x, b0.y);
-    mma_bf16_16816(c1, a1, b1.x, b1.y);
+  for (int n = 0; n < NT; ++n) {
+    bp[n] = reinterpret_cast<const uint2*>(tile[n]) + kh * 24 * 32 + lane;
+    c1[n][0] = c1[n][1] = c1[n][2] = c1[n][3] = 0.f;
   }
 #pragma unroll
-  for (int e = 0; e < 4; ++e) c[e] += c1[e];
+  for (int j = 0; j < 12; ++j) {
+    const uint32_t a0[4] = {a.lo[j].x, a.hi[j].x, a.lo[j].y, a.hi[j].y};
+    const uint32_t a1[4] = {a.lo[j].z, a.hi[j].z, a.lo[j].w, a.hi[j].w};
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const uint2 b0 = bp[n][(2 * j) * 32];
+      const uint2 b1 = bp[n][(2 * j + 1) * 32];
+      mma_bf16_16816(c[n], a0, b0.x, b0.y);
+      mma_bf16_16816(c1[n], a1, b1.x, b1.y);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[n][e] += c1[n][e];
 }
-
-// Sum of the two K halves: the kh = 1 warp parks its accumulator in shared memory, its kh = 0 partner adds it.
-// Returns true in the warp that owns the result.  `red` = [2 buffers][4 row tiles][32 lanes][4] floats.
-__device__ __forceinline__ bool mega_combine(float (&c)[4], float* red, int buf, int mt, int kh, int lane) {
-  float4* slot = reinterpret_cast<float4*>(red) + (buf * 4 + mt) * 32 + lane;
-  if (kh == 1) *slot = make_float4(c[0], c[1], c[2], c[3]);
+// Sum of the two K halves of NT tiles behind one named barrier: the kh = 1 warp parks its accumulators in shared memory,
+// its kh = 0 partner adds them.  Returns true in the warp that owns the result.  `red` = [2 buffers][3 tiles][4 row tiles][32 lanes] float4 (12 KB).
+template <int NT>
+__device__ __forceinline__ bool mega_combine_n(float (&c)[NT][4], float4* red, int buf, int mt, int kh, int lane) {
+  float4* slot = red + (buf * 12 + mt) * 32 + lane;
+  if (kh == 1) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) slot[n * 128] = make_float4(c[n][0], c[n][1], c[n][2], c[n][3]);
+  }
   named_bar_sync(2 + mt, 64);
   if (kh == 0) {
-    const float4 o = *slot;
-    c[0] += o.x; c[1] += o.y; c[2] += o.z; c[3] += o.w;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float4 o = slot[n * 128];
+      c[n][0] += o.x; c[n][1] += o.y; c[n][2] += o.z; c[n][3] += o.w;
+    }
   }
   return kh == 0;
 }
-
 // Two-way variant for the LM head: both warps of a pair end up with the sum (kh0 + kh1, the same operand order in both),
-// so that each can run the statistics of ONE of the two rows a thread owns.  `red2` = [2 buffers][8 warps][32 lanes][4] floats.
-__device__ __forceinline__ void mega_combine_both(float (&c)[4], float* red2, int buf, int warp, int mt, int kh, int lane) {
-  float4* mine = reinterpret_cast<float4*>(red2) + (buf * 8 + warp) * 32 + lane;
-  const float4* other = reinterpret_cast<const float4*>(red2) + (buf * 8 + (warp ^ 4)) * 32 + lane;
-  *mine = make_float4(c[0], c[1], c[2], c[3]);
+// so that each can run the statistics of ONE of the two rows a thread owns.  `red2` = [2 buffers][2 tiles][8 warps][32 lanes] float4.
+template <int NT>
+__device__ __forceinline__ void mega_combine_both_n(float (&c)[NT][4], float4* red2, int buf, int warp, int mt, int kh, int lane) {
+  float4* mine = red2 + (buf * 16 + warp) * 32 + lane;
+  const float4* other = red2 + (buf * 16 + (warp ^ 4)) * 32 + lane;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) mine[n * 256] = make_float4(c[n][0], c[n][1], c[n][2], c[n][3]);
   named_bar_sync(2 + mt, 64);
-  const float4 o = *other;
-  if (kh == 0) { c[0] += o.x; c[1] += o.y; c[2] += o.z; c[3] += o.w; }
-  else { c[0] = o.x + c[0]; c[1] = o.y + c[1]; c[2] = o.z + c[2]; c[3] = o.w + c[3]; }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const float4 o = other[n * 256];
+    if (kh == 0) { c[n][0] += o.x; c[n][1] += o.y; c[n][2] += o.z; c[n][3] += o.w; }
+    else { c[n][0] = o.x + c[n][0]; c[n][1] = o.y + c[n][1]; c[n][2] = o.z + c[n][2]; c[n][3] = o.w + c[n][3]; }
+  }
 }
 
 __device__ __forceinline__ float2 ldcg_f2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
@@ -246,8 +318,10 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   extern __shared__ __align__(1024) uint8_t mega_smem_raw[];
   uint8_t* smem = mega_smem_raw + ((1024u - (smem_u32(mega_smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;                                                  // 12 x 16 KB
-  float* red = reinterpret_cast<float*>(smem + kMegaSlots * kMegaSlotBytes);          // 2 x 8 x 32 x 4 floats = 8 KB
-  uint8_t* q_s = reinterpret_cast<uint8_t*>(red) + 8192;                 // per compute warp: 16 rows x 128 B (swizzled)
+  // 16 KB used by two phases that never overlap inside a CTA: attention -- per compute warp a 16-row x 128 B q tile
+  // (swizzled); GEMM phases -- the K-half exchange buffers of mega_combine_n / mega_combine_both_n
+  uint8_t* q_s = smem + kMegaSlots * kMegaSlotBytes;
+  float4* redv = reinterpret_cast<float4*>(q_s);
   float* att_part = reinterpret_cast<float*>(q_s + kMegaComputeWarps * 2048);   // scratch (LM head: this CTA's bias slice)
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(att_part) + 16 * 68 * 4);
   uint64_t* empty = full + kMegaSlots;
@@ -354,6 +428,15 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   MegaRing rg{ring, full, empty, 0u, p.error, issued};
   unsigned int* bar = p.barrier + (step & 1);
   unsigned int epoch = 0;
+  MegaTl tlf;
+  tlf.begin();
+#ifdef GITB200_TIMELINE
+#define MEGA_TL_ID(ph) ((l == 2) ? 710000 + (ph) * 100 : 0)
+#define MEGA_TL_DEP(a) if (((a).lo[11].w ^ (a).hi[11].w ^ (a).lo[0].x) == 0x9E3779B9u) *p.error = 99;
+#else
+#define MEGA_TL_ID(ph) 0
+#define MEGA_TL_DEP(a)
+#endif
   const int mt = warp & 3, kh = warp >> 2;
   const int g = lane >> 2, t = lane & 3;
   const int r0 = mt * 16 + g, r1 = r0 + 8;
@@ -364,17 +447,23 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     // ------------------------------------------------ P1: q | k | v ------------------------------------------------
     if (cta < 144) {
       MegaAFrag a;
+      if (MEGA_TL_ID(1)) tlf.mark(MEGA_TL_ID(1) + 0);
       mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
+      if (MEGA_TL_ID(1)) { tlf.mark(MEGA_TL_ID(1) + 1); MEGA_TL_DEP(a) tlf.mark(MEGA_TL_ID(1) + 2); }
       float2 bias_j[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) bias_j[j] = __ldg(reinterpret_cast<const float2*>(L.bqkv + (cta * 2 + j) * 8 + 2 * t));
+      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const uint8_t* tb[2] = {rg.acquire_ahead(0), rg.acquire_ahead(1)};
+      if (MEGA_TL_ID(1)) tlf.mark(MEGA_TL_ID(1) + 3);
+      mega_mma_tiles<2>(c, a, tb, kh, lane);
+      rg.release();
+      rg.release();
+      const bool own1 = mega_combine_n<2>(c, redv, red_buf, mt, kh, lane);
+      if (MEGA_TL_ID(1)) tlf.mark(MEGA_TL_ID(1) + 4);
+      if (own1) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint8_t* tb = rg.acquire();
-        mega_mma_tile(c, a, tb, kh, lane);
-        rg.release();
-        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+        for (int j = 0; j < 2; ++j) {
           const int f = (cta * 2 + j) * 8 + 2 * t;
           const float2 bias = bias_j[j];
           const int seg = f / kMegaD, fo = f - seg * kMegaD;
@@ -382,7 +471,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
           for (int hh = 0; hh < 2; ++hh) {
             const int r = hh ? r1 : r0;
             if (r >= R) continue;
-            const float v0 = c[2 * hh] + bias.x, v1 = c[2 * hh + 1] + bias.y;
+            const float v0 = c[j][2 * hh] + bias.x, v1 = c[j][2 * hh + 1] + bias.y;
             if (seg == 0) {
               *reinterpret_cast<uint32_t*>(p.qb + static_cast<long long>(r) * kMegaD + fo) = pack_bf16(v0 * 0.125f, v1 * 0.125f);
             } else {
@@ -391,10 +480,10 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
             }
           }
         }
-        red_buf ^= 1;
       }
+      red_buf ^= 1;
     }
-    mega_grid_sync(bar, epoch, p.error);
+    mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(1));
     // ------------------------------------------------ P2: attention ------------------------------------------------
     // `att_split` warps per (sequence, head) item (1 when the CTA has 5-8 items, up to 8 for small or long-sequence batches):
     // the item's 64-key chunks -- image K/V and text K/V, all through the ring -- are dealt to its warps round by round;
@@ -534,7 +623,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       }
       rg.idx = att_base + static_cast<uint32_t>(n_my_items) * rounds;
     }
-    mega_grid_sync(bar, epoch, p.error);
+    mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(2));
     // ------------------------------------------------ P3: attention output projection (+bias +residual) ------------------
     if (cta < 96) {
       MegaAFrag a;
@@ -544,22 +633,22 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       float2 xr[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};      // residual: requested before the MMA needs the tile
       if (kh == 0 && r0 < R) xr[0] = ldcg_f2(p.x + static_cast<long long>(r0) * kMegaD + f);
       if (kh == 0 && r1 < R) xr[1] = ldcg_f2(p.x + static_cast<long long>(r1) * kMegaD + f);
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint8_t* tb = rg.acquire();
-      mega_mma_tile(c, a, tb, kh, lane);
+      float c[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+      const uint8_t* tb[1] = {rg.acquire_ahead(0)};
+      mega_mma_tiles<1>(c, a, tb, kh, lane);
       rg.release();
-      if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+      if (mega_combine_n<1>(c, redv, red_buf, mt, kh, lane)) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int r = hh ? r1 : r0;
           if (r >= R) continue;
           *reinterpret_cast<float2*>(p.y + static_cast<long long>(r) * kMegaD + f) =
-              make_float2(xr[hh].x + (c[2 * hh] + bias.x), xr[hh].y + (c[2 * hh + 1] + bias.y));
+              make_float2(xr[hh].x + (c[0][2 * hh] + bias.x), xr[hh].y + (c[0][2 * hh + 1] + bias.y));
         }
       }
       red_buf ^= 1;
     }
-    mega_grid_sync(bar, epoch, p.error);
+    mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(3));
     // ------------------------------------------------ P4 / P7: LayerNorm(y) -> x, hb (one warp per row) -------------------
     // from_parts: the input row is x + ((p0 + p1) + p2) + p3 + bias (fc2's four k-slice partials, fixed order)
     auto layer_norm_rows = [&](const float* gamma, const float* beta, bool from_parts, const float* bias) {
@@ -619,21 +708,30 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       }
     };
     layer_norm_rows(L.lnag, L.lnab, false, nullptr);
-    mega_grid_sync(bar, epoch, p.error);
+    mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(4));
     // ------------------------------------------------ P5: fc1 + erf-GELU ------------------------------------------------
     if (cta < 128) {
       MegaAFrag a;
+      if (MEGA_TL_ID(5)) tlf.mark(MEGA_TL_ID(5) + 0);
       mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
+      if (MEGA_TL_ID(5)) { tlf.mark(MEGA_TL_ID(5) + 1); MEGA_TL_DEP(a) tlf.mark(MEGA_TL_ID(5) + 2); }
       float2 bias_j[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) bias_j[j] = __ldg(reinterpret_cast<const float2*>(L.b1 + (cta * 3 + j) * 8 + 2 * t));
+      float c[3][4];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint8_t* tb = rg.acquire();
-        mega_mma_tile(c, a, tb, kh, lane);
-        rg.release();
-        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+      for (int j = 0; j < 3; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+      const uint8_t* tb[3] = {rg.acquire_ahead(0), rg.acquire_ahead(1), rg.acquire_ahead(2)};
+      if (MEGA_TL_ID(5)) tlf.mark(MEGA_TL_ID(5) + 3);
+      mega_mma_tiles<3>(c, a, tb, kh, lane);
+      rg.release();
+      rg.release();
+      rg.release();
+      const bool own5 = mega_combine_n<3>(c, redv, red_buf, mt, kh, lane);
+      if (MEGA_TL_ID(5)) tlf.mark(MEGA_TL_ID(5) + 4);
+      if (own5) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
           const int f = (cta * 3 + j) * 8 + 2 * t;
           const float2 bias = bias_j[j];
 #pragma unroll
@@ -641,13 +739,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
             const int r = hh ? r1 : r0;
             if (r >= R) continue;
             *reinterpret_cast<uint32_t*>(p.ub + static_cast<long long>(r) * kMegaF + f) =
-                pack_bf16(apply_act(c[2 * hh] + bias.x, ACT_GELU_ERF), apply_act(c[2 * hh + 1] + bias.y, ACT_GELU_ERF));
+                pack_bf16(apply_act(c[j][2 * hh] + bias.x, ACT_GELU_ERF), apply_act(c[j][2 * hh + 1] + bias.y, ACT_GELU_ERF));
           }
         }
-        red_buf ^= 1;
       }
+      red_buf ^= 1;
     }
-    mega_grid_sync(bar, epoch, p.error);
+    mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(5));
     // ------------------------------------------------ P6: fc2, split over CTAs: 32 groups of 24 features x 4 k slices ------
     // (each CTA reads ONE 768-wide slice of the activations; the four partial sums of a feature meet, in slice order, in
     //  the LayerNorm phase below -- bit-reproducible, no atomics)
@@ -656,23 +754,27 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       MegaAFrag a;
       mega_load_a(a, p.ub + ks * kMegaD, kMegaF, R, mt, kh, lane);
       float* yp = p.ypart + static_cast<long long>(ks) * R * kMegaD;
+      float c[3][4];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint8_t* tb = rg.acquire();
-        mega_mma_tile(c, a, tb, kh, lane);
-        rg.release();
-        if (mega_combine(c, red, red_buf, mt, kh, lane)) {
+      for (int j = 0; j < 3; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+      const uint8_t* tb[3] = {rg.acquire_ahead(0), rg.acquire_ahead(1), rg.acquire_ahead(2)};
+      mega_mma_tiles<3>(c, a, tb, kh, lane);
+      rg.release();
+      rg.release();
+      rg.release();
+      if (mega_combine_n<3>(c, redv, red_buf, mt, kh, lane)) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
           const int f = (fg * 3 + j) * 8 + 2 * t;
-          if (r0 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r0) * kMegaD + f) = make_float2(c[0], c[1]);
-          if (r1 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r1) * kMegaD + f) = make_float2(c[2], c[3]);
+          if (r0 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r0) * kMegaD + f) = make_float2(c[j][0], c[j][1]);
+          if (r1 < R) *reinterpret_cast<float2*>(yp + static_cast<long long>(r1) * kMegaD + f) = make_float2(c[j][2], c[j][3]);
         }
-        red_buf ^= 1;
       }
+      red_buf ^= 1;
     }
-    mega_grid_sync(bar, epoch, p.error);
+    mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(6));
     layer_norm_rows(L.lnog, L.lnob, true, L.b2);
-    mega_grid_sync(bar, epoch, p.error);
+    mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(7));
   }
 
   // ------------------------------------------------ LM head with the greedy statistics folded in ---------------------------
@@ -698,31 +800,46 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     if (lm_n > 0) {
       MegaAFrag a;
       mega_load_a(a, p.hb, kMegaD, R, mt, kh, lane);
-      for (int j = 0; j < lm_n; ++j) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint8_t* tb = rg.acquire();
-        mega_mma_tile(c, a, tb, kh, lane);
-        rg.release();
-        mega_combine_both(c, red, red_buf, warp, mt, kh, lane);
-        red_buf ^= 1;
-        if (my_row < R) {
-          const int f = (lm_t0 + j) * 8 + 2 * t;
+      // statistics of one tile's two columns of this thread's row (columns arrive in increasing order)
+      auto lm_stats = [&](const float (&cc)[4], int j) {
+        if (my_row >= R) return;
+        const int f = (lm_t0 + j) * 8 + 2 * t;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = f + e;
-            if (col >= p.V) continue;
-            float v = c[2 * kh + e] + bias_s[j * 8 + 2 * t + e];
-            if (p.step_logits != nullptr) p.step_logits[(static_cast<long long>(step) * R + my_row) * p.V + col] = v;
-            if (!first && col == static_cast<int>(last)) v = -10000.0f;        // no-repeat (reference :330)
-            if (v > smax) {            // columns arrive in increasing order: the lowest index wins exact ties
-              ssum = ssum * __expf(smax - v) + 1.0f;
-              smax = v;
-              sarg = col;
-            } else {
-              ssum += __expf(v - smax);
-            }
+        for (int e = 0; e < 2; ++e) {
+          const int col = f + e;
+          if (col >= p.V) continue;
+          float v = (kh ? cc[2 + e] : cc[e]) + bias_s[j * 8 + 2 * t + e];
+          if (p.step_logits != nullptr) p.step_logits[(static_cast<long long>(step) * R + my_row) * p.V + col] = v;
+          if (!first && col == static_cast<int>(last)) v = -10000.0f;        // no-repeat (reference :330)
+          if (v > smax) {            // the lowest index wins exact ties
+            ssum = ssum * __expf(smax - v) + 1.0f;
+            smax = v;
+            sarg = col;
+          } else {
+            ssum += __expf(v - smax);
           }
         }
+      };
+      int j = 0;
+      for (; j + 2 <= lm_n; j += 2) {                 // two tiles in flight per warp (see mega_mma_tiles)
+        float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const uint8_t* tb[2] = {rg.acquire_ahead(0), rg.acquire_ahead(1)};
+        mega_mma_tiles<2>(c, a, tb, kh, lane);
+        rg.release();
+        rg.release();
+        mega_combine_both_n<2>(c, redv, red_buf, warp, mt, kh, lane);
+        red_buf ^= 1;
+        lm_stats(c[0], j);
+        lm_stats(c[1], j + 1);
+      }
+      if (j < lm_n) {
+        float c[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+        const uint8_t* tb[1] = {rg.acquire_ahead(0)};
+        mega_mma_tiles<1>(c, a, tb, kh, lane);
+        rg.release();
+        mega_combine_both_n<1>(c, redv, red_buf, warp, mt, kh, lane);
+        red_buf ^= 1;
+        lm_stats(c[0], j);
       }
     }
     // combine the 4 lanes of a quad (they hold the same row, interleaved column pairs)
@@ -744,8 +861,9 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       p.part_arg[static_cast<long long>(my_row) * G + cta] = sarg;
     }
   }
-  mega_grid_sync(bar, epoch, p.error);
+  mega_grid_sync(bar, epoch, p.error, tlf, 0);
 
+  tlf.end();
   // ------------------------------------------------ selection (greedy bookkeeping) + next token's embedding ----------------
   if (cta < R && warp == 0) {
     const int row = cta;
@@ -852,6 +970,6 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   }
 }
 
-constexpr size_t kMegaSmemBytes = 1024 + kMegaSlots * kMegaSlotBytes + 8192 + kMegaComputeWarps * 2048 + 16 * 68 * 4 + 2 * kMegaSlots * 8 + 64 + 64;
+constexpr size_t kMegaSmemBytes = 1024 + kMegaSlots * kMegaSlotBytes + kMegaComputeWarps * 2048 + 16 * 68 * 4 + 2 * kMegaSlots * 8 + 64 + 64;
 
 }  // namespace gitb200

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Round 2, call 17: multi-tile GEMM phases of decode_mega_kernel -- parity subset, bench config 2 / 4, in-kernel timeline.
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "one_kernel or reproducible or config2 or config4 or decisive or teacher or eos_forcing or prefix" > gpurun_out/r2_tests17.log 2>&1
+tail -n 3 gpurun_out/r2_tests17.log
+timeout 200 python bench.py --no-cpu-baseline --no-micro --no-serving > gpurun_out/r2_bench17_c2.json 2> gpurun_out/r2_bench17_c2.err
+tail -n 2 gpurun_out/r2_bench17_c2.err | cut -c1-200; cut -c1-330 gpurun_out/r2_bench17_c2.json
+timeout 200 python bench.py --config 4 --no-cpu-baseline --no-micro --no-serving > gpurun_out/r2_bench17_c4.json 2> gpurun_out/r2_bench17_c4.err
+cut -c1-330 gpurun_out/r2_bench17_c4.json
+GITB200_TIMELINE=1 timeout 200 python -c "from generativeimage2text_b200 import build; build.build(force=True)" > gpurun_out/r2_tlbuild17.log 2>&1
+timeout 120 python tools/mega_timeline.py > gpurun_out/r2_mega_timeline17.txt 2>&1
+sed -n 1,16p gpurun_out/r2_mega_timeline17.txt; tail -n 4 gpurun_out/r2_mega_timeline17.txt

@@ -28,9 +28,19 @@ with torch.cuda.stream(s):
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * (2 * 8192))()
     n = lib.gitb200_debug_timeline(0, buf, 8192)
-ev = sorted((buf[2 * i], int(buf[2 * i + 1])) for i in range(n))
-ev = [(t, k) for t, k in ev if k >= 500000]
-# one step = 44 barriers: take the 10th step
+raw = [(buf[2 * i], int(buf[2 * i + 1])) for i in range(n)]
+# fine marks: per launch a 160-entry slice of (%clock64, id) pairs opened by id 700000 (see MegaTl in decode_mega.cuh)
+fine, coarse, i = [], [], 0
+while i < len(raw):
+    if raw[i][1] == 700000:
+        fine.append([e for e in raw[i:i + 160] if e[1] != 0])
+        i += 160
+    else:
+        if raw[i][1] != 0:
+            coarse.append(raw[i])
+        i += 1
+ev = sorted(e for e in coarse if e[1] >= 500000)
+# one step = 44 barriers (the fine-marked layer 2 logs its barriers through the slice instead): take the 10th step
 starts = [i for i, (t, k) in enumerate(ev) if k == 500001]
 a, b = starts[10], starts[11]
 names = ['qkv', 'attn', 'oproj', 'ln1', 'fc1', 'fc2', 'ln2']
@@ -43,3 +53,17 @@ for t, k in ev[a:b]:
     print('%9.2f us (+%6.2f)  %s barrier %2d after %s' % ((t - t0) * 1e-3, (t - prev) * 1e-3, what, n_bar, lbl))
     prev = t
 print('step total: %.2f us' % ((ev[b][0] - t0) * 1e-3))
+if len(fine) > 10:
+    sl = dict((k, t) for t, k in fine[10])
+    if all(k in sl for k in (700000, 700001, 700002, 700003)):
+        ns_per_clk = (sl[700003] - sl[700001]) / float(sl[700002] - sl[700000])
+        print('\nlayer 2 of that step, thread 0 of CTA 0 (clock64 marks, %.3f ns per clock):' % ns_per_clk)
+        sub = {0: 'phase start', 1: 'A loads issued', 2: 'A loads landed', 3: 'weight tiles landed', 4: 'MMAs + K-half exchange done',
+               5: 'epilogue issued', 6: 'all compute warps of the CTA at the barrier', 7: 'fence done', 8: 'red.release issued',
+               9: 'barrier released', 10: 'CTA released'}
+        marks = sorted((t, k) for t, k in fine[10] if 710000 <= k < 720000)
+        prev = marks[0][0] if marks else 0
+        for t, k in marks:
+            ph, sb = (k - 710000) // 100, (k - 710000) % 100
+            print('  %-6s %-46s +%6.2f us' % (names[ph - 1], sub.get(sb, str(sb)), (t - prev) * ns_per_clk * 1e-3))
+            prev = t
