@@ -5,7 +5,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libgitb200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int, c_int64, c_float, c_char_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_char_p
 c_ll = ctypes.c_longlong
@@ -56,6 +56,8 @@ SIGNATURES = {
     'gitb200_generate_finish': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_int32)]),
     'gitb200_last_decode_ms': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     'gitb200_set_row_prefixes': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'gitb200_set_trie': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    'gitb200_set_sampling': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float]),
     'gitb200_launch_count': (c_int64, [c_void_p]),
     'gitb200_set_option': (c_int, [c_void_p, c_char_p, c_int64]),
     'gitb200_preproc_create': (c_int, [c_int, ctypes.POINTER(c_void_p)]),

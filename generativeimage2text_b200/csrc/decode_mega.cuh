@@ -18,7 +18,8 @@
 //   * weights are stationary per CTA: a GEMM phase gives CTA c a few 8-feature tiles over a 768-long reduction; the 8 warps
 //     split a tile 4 row tiles x 2 K halves.  fc2 (K = 3072) is dealt as 4 k slices x 96 feature tiles over 128 CTAs, its
 //     four partial sums meet in slice order in the LayerNorm phase: no atomics anywhere, the step is bit-reproducible;
-//   * attention: `att_split` warps per (sequence, head) item, 64 keys per ring slot, online softmax, fixed-order merge.
+//   * attention: the 64-key chunks of a CTA's (sequence, head) items are dealt round-robin to its 8 warps, online-softmax
+//     states in shared memory, fixed-order merge.
 // The skinny GEMMs and the 1-row attention are HBM-bound byte work (arithmetic intensity ~rows FLOP/B): they use the
 // warp-level mma.sync path fed from shared memory (measured limit here: ~0.77 us per 64 x 8 x 768 tile per SM, which is
 // what the 26-tile LM-head slice of a CTA costs); tcgen05 / TMEM stay with the compute-bound encoder and prefill GEMMs:
@@ -39,6 +40,8 @@ constexpr int kMegaTileBytes = 12288;      // 8 output features x 768 k x bf16, 
 constexpr int kMegaKvRows = 64;            // keys per attention chunk: one ring slot = K box (8 KB) | V box (8 KB)
 constexpr int kMegaMaxRows = 64;
 constexpr int kMegaD = 768, kMegaF = 3072, kMegaH = 12;
+constexpr int kMegaAttItems = 6;           // (sequence, head) attention items of the busiest CTA: ceil(64 * 12 / 148)
+constexpr int kMegaAttState = 72;          // floats per (item, warp) softmax state: 64 output dims, running max, 4 lane sums
 constexpr unsigned int kMegaSpinLimit = 1u << 18;   // bounded waits: a protocol bug must end in an error code, not a hung device
 
 struct MegaLayer {
@@ -60,7 +63,6 @@ struct MegaParams {
   const float* positions;  // fp32 [max_pos, 768]
   const float* lnemb_g; const float* lnemb_b;
   int R, M, T_alloc, V, n_layers;
-  int att_split;           // warps per attention item (1, 2, 4 or 8; host: as many as the CTA's item count leaves room for)
   // activations (global, L2 resident)
   float* x;                // [R, 768] residual stream (post-LayerNorm)
   float* y;                // [R, 768] pre-LayerNorm sum (after the attention block)
@@ -81,9 +83,11 @@ struct MegaParams {
 
 // ---- packing: [N, K] row-major bf16 -> tiles of 8 features x 768 k in fragment order ------------------------------------
 // Tile layout: 48 k-steps x 32 lanes x 8 bytes.  Lane (g = lane / 4, t = lane % 4) of k-step s holds the four k values
-// k0 + 32 * (s / 2) + 8 t + 4 (s % 2) + {0, 1, 2, 3} of feature 8 tile + g: the B fragment (b0 = first pair, b1 = second
-// pair) of an m16n8k16 MMA whose k index has been permuted so that the matching A fragment is 8 CONTIGUOUS bf16 per
-// thread and k-step pair (one 128-bit load from the row-major activation matrix).
+// k0 + 64 * (s / 4) + 16 t + 4 (s % 4) + {0, 1, 2, 3} of feature 8 tile + g: the B fragment (b0 = first pair, b1 = second
+// pair) of an m16n8k16 MMA whose k index has been permuted so that the matching A fragment is 16 CONTIGUOUS bf16 per
+// thread and group of four k-steps -- one 256-bit load from the row-major activation matrix, and the four lanes of a row
+// together fetch one whole 128-byte line (with 128-bit loads every line was touched by two instructions, and the L1
+// wavefronts of the A loads, not L2 bandwidth, set the pace of the GEMM phases: profiles/decode_mega_timeline_r02_call18.txt).
 __global__ void __launch_bounds__(256) pack_tiles_kernel(const __nv_bfloat16* __restrict__ W, long long ldw, int n_feat, int k0,
                                                          uint8_t* __restrict__ dst, long long n_tiles, int tile_stride_tiles,
                                                          int tile_offset) {
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(256) pack_tiles_kernel(const __nv_bfloat16* __
     const long long tile = i / (48 * 32);
     const int g = lane >> 2, t = lane & 3;
     const long long f = tile * 8 + g;
-    const int k = k0 + 32 * (s >> 1) + 8 * t + 4 * (s & 1);
+    const int k = k0 + 64 * (s >> 2) + 16 * t + 4 * (s & 3);
     uint2 v = make_uint2(0u, 0u);
     if (f < n_feat) v = *reinterpret_cast<const uint2*>(W + f * ldw + k);
     *reinterpret_cast<uint2*>(dst + (tile * tile_stride_tiles + tile_offset) * kMegaTileBytes + (s * 32 + lane) * 8) = v;
@@ -210,7 +214,9 @@ __device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned i
     epoch += gridDim.x;
     if (tl_id) tlf.mark(tl_id + 6);                                 // all compute warps of the CTA are here
     else tl_mark_one(500000 + static_cast<int>(epoch / gridDim.x)); // this CTA arrived at barrier #n
-    __threadfence();
+    // release-RMW at gpu scope: cumulative over the CTA's writes that the bar.sync above ordered before this thread, so
+    // no separate fence -- __threadfence() is a sequentially-consistent fence (MEMBAR.SC.GPU + L1 invalidate) that cost
+    // 0.5-2.5 us per barrier here on top of the release's own MEMBAR.ALL.GPU
     if (tl_id) tlf.mark(tl_id + 7);
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
     if (tl_id) tlf.mark(tl_id + 8);
@@ -230,18 +236,31 @@ __device__ __forceinline__ void mega_grid_sync(unsigned int* counter, unsigned i
 
 // A operand of one GEMM phase: this warp's 16 rows x 384 k of a row-major bf16 activation matrix, straight from L2.
 struct MegaAFrag {
-  uint4 lo[12];   // row g     : 8 contiguous k per entry (two k-steps)
-  uint4 hi[12];   // row g + 8
+  uint32_t lo[6][8];   // row g     : 16 contiguous k per entry (four k-steps)
+  uint32_t hi[6][8];   // row g + 8
 };
+__device__ __forceinline__ void ldcg_256(uint32_t (&r)[8], const void* p) {
+  asm volatile("ld.global.cg.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void mega_load_a(MegaAFrag& a, const __nv_bfloat16* A, long long lda, int rows, int mt, int kh, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int r0 = mt * 16 + g, r1 = r0 + 8;
-  const uint4* p0 = reinterpret_cast<const uint4*>(A + static_cast<long long>(r0) * lda + kh * 384 + 8 * t);
-  const uint4* p1 = reinterpret_cast<const uint4*>(A + static_cast<long long>(r1) * lda + kh * 384 + 8 * t);
+  const __nv_bfloat16* p0 = A + static_cast<long long>(r0) * lda + kh * 384 + 16 * t;
+  const __nv_bfloat16* p1 = A + static_cast<long long>(r1) * lda + kh * 384 + 16 * t;
 #pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    a.lo[j] = (r0 < rows) ? __ldcg(p0 + 4 * j) : make_uint4(0, 0, 0, 0);
-    a.hi[j] = (r1 < rows) ? __ldcg(p1 + 4 * j) : make_uint4(0, 0, 0, 0);
+  for (int j = 0; j < 6; ++j) {
+    if (r0 < rows) ldcg_256(a.lo[j], p0 + 64 * j);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.lo[j][e] = 0u;
+    }
+    if (r1 < rows) ldcg_256(a.hi[j], p1 + 64 * j);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.hi[j][e] = 0u;
+    }
   }
 }
 // c += A(16 x 384 of this warp) * tile(8 features, this warp's k half), NT tiles at once.  Per tile two independent
@@ -258,15 +277,18 @@ __device__ __forceinline__ void mega_mma_tiles(float (&c)[NT][4], const MegaAFra
     c1[n][0] = c1[n][1] = c1[n][2] = c1[n][3] = 0.f;
   }
 #pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    const uint32_t a0[4] = {a.lo[j].x, a.hi[j].x, a.lo[j].y, a.hi[j].y};
-    const uint32_t a1[4] = {a.lo[j].z, a.hi[j].z, a.lo[j].w, a.hi[j].w};
+  for (int j = 0; j < 6; ++j) {
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const uint2 b0 = bp[n][(2 * j) * 32];
-      const uint2 b1 = bp[n][(2 * j + 1) * 32];
-      mma_bf16_16816(c[n], a0, b0.x, b0.y);
-      mma_bf16_16816(c1[n], a1, b1.x, b1.y);
+    for (int i = 0; i < 4; i += 2) {
+      const uint32_t a0[4] = {a.lo[j][2 * i], a.hi[j][2 * i], a.lo[j][2 * i + 1], a.hi[j][2 * i + 1]};
+      const uint32_t a1[4] = {a.lo[j][2 * i + 2], a.hi[j][2 * i + 2], a.lo[j][2 * i + 3], a.hi[j][2 * i + 3]};
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const uint2 b0 = bp[n][(4 * j + i) * 32];
+        const uint2 b1 = bp[n][(4 * j + i + 1) * 32];
+        mma_bf16_16816(c[n], a0, b0.x, b0.y);
+        mma_bf16_16816(c1[n], a1, b1.x, b1.y);
+      }
     }
   }
 #pragma unroll
@@ -322,8 +344,11 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   // (swizzled); GEMM phases -- the K-half exchange buffers of mega_combine_n / mega_combine_both_n
   uint8_t* q_s = smem + kMegaSlots * kMegaSlotBytes;
   float4* redv = reinterpret_cast<float4*>(q_s);
-  float* att_part = reinterpret_cast<float*>(q_s + kMegaComputeWarps * 2048);   // scratch (LM head: this CTA's bias slice)
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(att_part) + 16 * 68 * 4);
+  // attention: softmax states [item][warp][kMegaAttState floats], then the staged q rows of the CTA's items; the LM head keeps
+  // this CTA's bias slice here
+  float* att_part = reinterpret_cast<float*>(q_s + kMegaComputeWarps * 2048);
+  uint4* q_stage = reinterpret_cast<uint4*>(att_part + kMegaAttItems * kMegaComputeWarps * kMegaAttState);     // [items][8] x 16 B
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(q_stage) + kMegaAttItems * 128);
   uint64_t* empty = full + kMegaSlots;
   volatile uint32_t* issued = reinterpret_cast<volatile uint32_t*>(empty + kMegaSlots);
 
@@ -387,32 +412,28 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       for (int l = 0; l < p.n_layers; ++l) {
         const MegaLayer& L = p.layer[l];
         if (cta < 144) for (int j = 0; j < 2; ++j) tile(L.wqkv + static_cast<size_t>(cta * 2 + j) * kMegaTileBytes);
-        // attention chunks of this CTA's items, ROUND-ROBIN over the items (each item is walked by its own warp, see the
-        // consumer): round r = image keys 64r .. 64r + 63 of every item, then the text rounds, `att_slots` items at a time.
-        const int att_slots = kMegaComputeWarps / p.att_split;      // items walked concurrently (see the consumer)
-        for (int k0 = 0; k0 < n_my_items; k0 += att_slots) {
-          const int kn = min(att_slots, n_my_items - k0);
-          for (int r = 0; r < n_kv + n_txt; ++r) {
-            if (r == n_kv) {
-              // the text K/V of position `pos` exist once every CTA has passed barrier 7l + 1 (after this layer's QKV phase)
-              const unsigned int target = static_cast<unsigned int>(G) * (7u * l + 1u);
-              unsigned int spins = 0;
-              while (ld_acquire_gpu(p.barrier + (step & 1)) < target) {
-                if (++spins > kMegaSpinLimit || ((spins & 255u) == 255u && *reinterpret_cast<const volatile int*>(p.error) != 0)) {
-                  if (*reinterpret_cast<const volatile int*>(p.error) == 0) *p.error = 4;
-                  break;
-                }
+        // attention chunks ("units") of this CTA's items, round-major: unit u = r * n_my_items + k is keys 64r .. 64r + 63 of
+        // item k (image keys first, then the text rounds); the consumer deals the units to its 8 warps round-robin
+        for (int r = 0; r < n_kv + n_txt; ++r) {
+          if (r == n_kv) {
+            // the text K/V of position `pos` exist once every CTA has passed barrier 7l + 1 (after this layer's QKV phase)
+            const unsigned int target = static_cast<unsigned int>(G) * (7u * l + 1u);
+            unsigned int spins = 0;
+            while (ld_acquire_gpu(p.barrier + (step & 1)) < target) {
+              if (++spins > kMegaSpinLimit || ((spins & 255u) == 255u && *reinterpret_cast<const volatile int*>(p.error) != 0)) {
+                if (*reinterpret_cast<const volatile int*>(p.error) == 0) *p.error = 4;
+                break;
               }
-              asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> this thread's TMA reads
             }
-            for (int kk = 0; kk < kn; ++kk) {
-              const int item = my_cta_rev + (k0 + kk) * G;
-              const int b = item / kMegaH, h = item - b * kMegaH;
-              if (r < n_kv)
-                kv_pair(&tmKV, (l * 2 + 0) * R * M + b * M + r * kMegaKvRows, (l * 2 + 1) * R * M + b * M + r * kMegaKvRows, h * 64);
-              else
-                kv_pair(&tmTXT, ((l * 2 + 0) * R + b) * p.T_alloc + (r - n_kv) * 64, ((l * 2 + 1) * R + b) * p.T_alloc + (r - n_kv) * 64, h * 64);
-            }
+            asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> this thread's TMA reads
+          }
+          for (int kk = 0; kk < n_my_items; ++kk) {
+            const int item = my_cta_rev + kk * G;
+            const int b = item / kMegaH, h = item - b * kMegaH;
+            if (r < n_kv)
+              kv_pair(&tmKV, (l * 2 + 0) * R * M + b * M + r * kMegaKvRows, (l * 2 + 1) * R * M + b * M + r * kMegaKvRows, h * 64);
+            else
+              kv_pair(&tmTXT, ((l * 2 + 0) * R + b) * p.T_alloc + (r - n_kv) * 64, ((l * 2 + 1) * R + b) * p.T_alloc + (r - n_kv) * 64, h * 64);
           }
         }
         if (cta < 96) tile(L.wo + static_cast<size_t>(cta) * kMegaTileBytes);
@@ -432,7 +453,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   tlf.begin();
 #ifdef GITB200_TIMELINE
 #define MEGA_TL_ID(ph) ((l == 2) ? 710000 + (ph) * 100 : 0)
-#define MEGA_TL_DEP(a) if (((a).lo[11].w ^ (a).hi[11].w ^ (a).lo[0].x) == 0x9E3779B9u) *p.error = 99;
+#define MEGA_TL_DEP(a) if (((a).lo[5][7] ^ (a).hi[5][7] ^ (a).lo[0][0]) == 0x9E3779B9u) *p.error = 99;
 #else
 #define MEGA_TL_ID(ph) 0
 #define MEGA_TL_DEP(a)
@@ -485,34 +506,41 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     }
     mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(1));
     // ------------------------------------------------ P2: attention ------------------------------------------------
-    // `att_split` warps per (sequence, head) item (1 when the CTA has 5-8 items, up to 8 for small or long-sequence batches):
-    // the item's 64-key chunks -- image K/V and text K/V, all through the ring -- are dealt to its warps round by round;
-    // S = q K^T and O += P V run on mma.sync with a 16-row q tile whose row 0 is the query (rows 1..15 zero) and an online
-    // softmax per 64 keys; the warps of an item merge their softmax states through shared memory.  No block-wide barrier.
+    // The CTA's 5-6 (sequence, head) items x (image + text) 64-key chunks form U units; warp w takes units w, w + 8, ...
+    // (whatever item they belong to), so the tensor pipes of the four SM sub-partitions carry the same load -- one warp
+    // per item left two of them with twice the MMAs of the others, and mma.sync issue rate is what bounds this phase.
+    // The online-softmax state of (item, warp) lives in shared memory between the units of a warp; S = q K^T and
+    // O += P V run on mma.sync with a 16-row q tile whose row 0 is the query (rows 1..15 zero).  At the end warp k merges
+    // the 8 states of item k in warp order (bit-reproducible).  Two block-level barriers per phase, none per unit.
     {
-      const int rounds = n_kv + n_txt;                      // ring chunks per item (64 keys each), dealt round-robin
+      const int rounds = n_kv + n_txt;                      // ring chunks per item (64 keys each)
       const uint32_t att_base = rg.idx;
+      const int U = n_my_items * rounds;
       uint8_t* qw = q_s + warp * 2048;
       constexpr float kLog2e = 1.44269504088896340736f;
-      const int W = p.att_split, att_slots = kMegaComputeWarps / W;
-      const int slot = warp / W, part = warp - slot * W;
-      for (int k0 = 0; k0 < n_my_items; k0 += att_slots) {
-        const int kn = min(att_slots, n_my_items - k0);
-        if (slot >= kn) continue;
-        const int k = k0 + slot;
-        const int item = my_cta_rev + k * G;
-        const int b = item / kMegaH, h = item - b * kMegaH;
-        // q tile (already scaled by 1/8), 128B-swizzled like the K/V boxes: lanes 0..7 fetch row 0, everything else is zero
-        {
-          uint4 qv = make_uint4(0, 0, 0, 0);
-          if (lane < 8) qv = __ldcg(reinterpret_cast<const uint4*>(p.qb + static_cast<long long>(b) * kMegaD + h * 64) + lane);
+      // phase start: this warp's q tile zeroed (row 0 is rewritten per unit), its softmax states reset, the q rows staged
 #pragma unroll
-          for (int jq = 0; jq < 4; ++jq) {
-            const int cell = lane + 32 * jq, row = cell >> 3, ch = cell & 7;
-            *reinterpret_cast<uint4*>(qw + row * 128 + ((ch ^ (row & 7)) << 4)) = (row == 0) ? qv : make_uint4(0, 0, 0, 0);
-          }
-          __syncwarp();
+      for (int jq = 0; jq < 4; ++jq) reinterpret_cast<uint4*>(qw)[lane + 32 * jq] = make_uint4(0, 0, 0, 0);
+      if (lane < 4) {
+        for (int k = 0; k < n_my_items; ++k) {
+          float* sl = att_part + (k * kMegaComputeWarps + warp) * kMegaAttState;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { sl[8 * j + 2 * lane] = 0.f; sl[8 * j + 2 * lane + 1] = 0.f; }
+          sl[65 + lane] = 0.f;
+          if (lane == 0) sl[64] = -INFINITY;
         }
+      }
+      if (warp < n_my_items && lane < 8) {
+        const int item = my_cta_rev + warp * G;
+        const int b = item / kMegaH, h = item - b * kMegaH;
+        q_stage[warp * 8 + lane] = __ldcg(reinterpret_cast<const uint4*>(p.qb + static_cast<long long>(b) * kMegaD + h * 64) + lane);
+      }
+      named_bar_sync(1, kMegaComputeWarps * 32);
+      for (int u = warp; u < U; u += kMegaComputeWarps) {
+        const int r = u / n_my_items, k = u - r * n_my_items;
+        // q tile (already scaled by 1/8), 128B-swizzled like the K/V boxes: row 0 <- the item's q (chunk c of row 0 sits at c << 4)
+        if (lane < 8) *reinterpret_cast<uint4*>(qw + (lane << 4)) = q_stage[k * 8 + lane];
+        __syncwarp();
         uint32_t qa[4][4];
         {
           const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -522,10 +550,17 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
             ldmatrix_x4(qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], smem_u32(qw) + row * 128 + ((chunk ^ (row & 7)) << 4));
           }
         }
+        float* sl = att_part + (k * kMegaComputeWarps + warp) * kMegaAttState;
         float o[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;       // row g of the q tile (only g == 0 is a real row)
+        if (g == 0) {
+          m_run = sl[64];
+          l_run = sl[65 + t];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o[j][0] = sl[8 * j + 2 * t]; o[j][1] = sl[8 * j + 2 * t + 1]; }
+        }
         // 64 keys: rows [row0, row0 + 64) of a K box at sK and of a V box at sV; key index = key0 + row, valid below key_end
         auto keys64 = [&](uint32_t sK, uint32_t sV, int row0, int key0, int key_end) {
           float sc[8][4];
@@ -554,15 +589,15 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
           const float m_new = fmaxf(m_run, mx);
           const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-          const float corr = exp2f((m_run - m_use) * kLog2e);
+          const float corr = ex2_approx((m_run - m_use) * kLog2e);
           m_run = m_new;
           l_run *= corr;
 #pragma unroll
           for (int j = 0; j < 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {                  // 16 keys per k-step = score tiles 2kk, 2kk + 1
-            const float p0 = exp2f((sc[2 * kk][0] - m_use) * kLog2e), p1 = exp2f((sc[2 * kk][1] - m_use) * kLog2e);
-            const float p2 = exp2f((sc[2 * kk + 1][0] - m_use) * kLog2e), p3 = exp2f((sc[2 * kk + 1][1] - m_use) * kLog2e);
+            const float p0 = ex2_approx((sc[2 * kk][0] - m_use) * kLog2e), p1 = ex2_approx((sc[2 * kk][1] - m_use) * kLog2e);
+            const float p2 = ex2_approx((sc[2 * kk + 1][0] - m_use) * kLog2e), p3 = ex2_approx((sc[2 * kk + 1][1] - m_use) * kLog2e);
             l_run += (p0 + p1) + (p2 + p3);
             const uint32_t pa[4] = {pack_bf16(p0, p1), 0u, pack_bf16(p2, p3), 0u};   // rows 8..15 of the q tile do not exist
             const int vrow = row0 + 16 * kk + ((lane >> 3) & 1) * 8 + (lane & 7);
@@ -576,52 +611,39 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
             }
           }
         };
-        // chunk (item k, round r) sits at  att_base + [items of earlier groups] * rounds + r * kn + slot
-        const uint32_t c0 = att_base + static_cast<uint32_t>(k0) * rounds + slot;
-        for (int r = part; r < rounds; r += W) {
-          const uint32_t ci = c0 + static_cast<uint32_t>(r) * kn;
-          const uint32_t sK = smem_u32(rg.acquire_at(ci));
-          if (r < n_kv) keys64(sK, sK + 8192, 0, r * kMegaKvRows, M);               // image keys 64r ..
-          else keys64(sK, sK + 8192, 0, (r - n_kv) * 64, pos + 1);                 // text positions 64(r - n_kv) ..
-          rg.release_at(ci);
-        }
-        l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-        l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-        if (W == 1) {
-          if (g == 0) {
-            const float inv = 1.0f / l_run;
-            __nv_bfloat16* dst = p.ctx + static_cast<long long>(b) * kMegaD + h * 64 + 2 * t;
+        const uint32_t ci = att_base + static_cast<uint32_t>(u);
+        const uint32_t sK = smem_u32(rg.acquire_at(ci));
+        if (r < n_kv) keys64(sK, sK + 8192, 0, r * kMegaKvRows, M);               // image keys 64r ..
+        else keys64(sK, sK + 8192, 0, (r - n_kv) * 64, pos + 1);                 // text positions 64(r - n_kv) ..
+        rg.release_at(ci);
+        if (g == 0) {
+          if (t == 0) sl[64] = m_run;
+          sl[65 + t] = l_run;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16(o[j][0] * inv, o[j][1] * inv);
-          }
-        } else {
-          // merge the W softmax states of this item (fixed order: bit-reproducible)
-          float* pp = att_part + warp * 68;
-          if (g == 0) {
-            if (t == 0) { pp[64] = m_run; pp[65] = l_run; }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { pp[8 * j + 2 * t] = o[j][0]; pp[8 * j + 2 * t + 1] = o[j][1]; }
-          }
-          named_bar_sync(6 + slot, W * 32);
-          if (part == 0) {
-            const float* p0 = att_part + (slot * W) * 68;
-            float mm = -INFINITY;
-            for (int i = 0; i < W; ++i) mm = fmaxf(mm, p0[i * 68 + 64]);
-            float lsum = 0.f, a0 = 0.f, a1 = 0.f;
-            for (int i = 0; i < W; ++i) {
-              const float mi = p0[i * 68 + 64];
-              const float wgt = (mi == -INFINITY) ? 0.f : exp2f((mi - mm) * kLog2e);
-              lsum += p0[i * 68 + 65] * wgt;
-              a0 += p0[i * 68 + 2 * lane] * wgt;
-              a1 += p0[i * 68 + 2 * lane + 1] * wgt;
-            }
-            *reinterpret_cast<uint32_t*>(p.ctx + static_cast<long long>(b) * kMegaD + h * 64 + 2 * lane) = pack_bf16(a0 / lsum, a1 / lsum);
-          }
-          named_bar_sync(6 + slot, W * 32);                 // the partial states are rewritten by the item's next group
+          for (int j = 0; j < 8; ++j) { sl[8 * j + 2 * t] = o[j][0]; sl[8 * j + 2 * t + 1] = o[j][1]; }
         }
-        __syncwarp();                                       // the q tile is rewritten by this warp's next item
+        __syncwarp();                                       // the q tile's row 0 and the state are rewritten by the next unit
       }
-      rg.idx = att_base + static_cast<uint32_t>(n_my_items) * rounds;
+      named_bar_sync(1, kMegaComputeWarps * 32);
+      if (warp < n_my_items) {
+        // merge the 8 softmax states of item `warp` (fixed order: bit-reproducible); lane -> output dims 2 lane, 2 lane + 1
+        const int item = my_cta_rev + warp * G;
+        const int b = item / kMegaH, h = item - b * kMegaH;
+        const float* p0 = att_part + (warp * kMegaComputeWarps) * kMegaAttState;
+        float mm = -INFINITY;
+        for (int i = 0; i < kMegaComputeWarps; ++i) mm = fmaxf(mm, p0[i * kMegaAttState + 64]);
+        float lsum = 0.f, a0 = 0.f, a1 = 0.f;
+        for (int i = 0; i < kMegaComputeWarps; ++i) {
+          const float* pi = p0 + i * kMegaAttState;
+          const float mi = pi[64];
+          const float wgt = (mi == -INFINITY) ? 0.f : exp2f((mi - mm) * kLog2e);
+          lsum += ((pi[65] + pi[66]) + (pi[67] + pi[68])) * wgt;
+          a0 += pi[2 * lane] * wgt;
+          a1 += pi[2 * lane + 1] * wgt;
+        }
+        *reinterpret_cast<uint32_t*>(p.ctx + static_cast<long long>(b) * kMegaD + h * 64 + 2 * lane) = pack_bf16(a0 / lsum, a1 / lsum);
+      }
+      rg.idx = att_base + static_cast<uint32_t>(U);
     }
     mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(2));
     // ------------------------------------------------ P3: attention output projection (+bias +residual) ------------------
@@ -649,11 +671,11 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       red_buf ^= 1;
     }
     mega_grid_sync(bar, epoch, p.error, tlf, MEGA_TL_ID(3));
-    // ------------------------------------------------ P4 / P7: LayerNorm(y) -> x, hb (one warp per row) -------------------
+    // ------------------------------------------------ P4 / P7: LayerNorm(y) -> x, hb (warp 0 of CTA r: row r) ----------------
     // from_parts: the input row is x + ((p0 + p1) + p2) + p3 + bias (fc2's four k-slice partials, fixed order)
     auto layer_norm_rows = [&](const float* gamma, const float* beta, bool from_parts, const float* bias) {
-      const int row = cta * kMegaComputeWarps + warp;
-      if (row < R) {
+      const int row = cta;           // one row per CTA (R <= 64 of them): 8 rows per CTA made 8 SMs pull all the rows through their L2 ports
+      if (row < R && warp == 0) {
         float4 v[6];
         if (!from_parts) {
           const float4* yp = reinterpret_cast<const float4*>(p.y + static_cast<long long>(row) * kMegaD);
@@ -821,16 +843,20 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         }
       };
       int j = 0;
+      MEGA_TL(720000);                                // LM head: A loads issued
       for (; j + 2 <= lm_n; j += 2) {                 // two tiles in flight per warp (see mega_mma_tiles)
         float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const uint8_t* tb[2] = {rg.acquire_ahead(0), rg.acquire_ahead(1)};
+        MEGA_TL(720100 + j);                          // the pair's tiles landed
         mega_mma_tiles<2>(c, a, tb, kh, lane);
         rg.release();
         rg.release();
         mega_combine_both_n<2>(c, redv, red_buf, warp, mt, kh, lane);
+        MEGA_TL(720200 + j);                          // MMAs + exchange done
         red_buf ^= 1;
         lm_stats(c[0], j);
         lm_stats(c[1], j + 1);
+        MEGA_TL(720300 + j);                          // statistics done
       }
       if (j < lm_n) {
         float c[1][4] = {{0.f, 0.f, 0.f, 0.f}};
@@ -970,6 +996,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   }
 }
 
-constexpr size_t kMegaSmemBytes = 1024 + kMegaSlots * kMegaSlotBytes + kMegaComputeWarps * 2048 + 16 * 68 * 4 + 2 * kMegaSlots * 8 + 64 + 64;
+constexpr size_t kMegaSmemBytes = 1024 + kMegaSlots * kMegaSlotBytes + kMegaComputeWarps * 2048 +
+                                  kMegaAttItems * kMegaComputeWarps * kMegaAttState * 4 + kMegaAttItems * 128 + 2 * kMegaSlots * 8 + 64 + 64;
 
 }  // namespace gitb200

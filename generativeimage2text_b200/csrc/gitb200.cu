@@ -28,6 +28,7 @@
 
 #include "../../include/gitb200.h"
 #include "attention.cuh"
+#include "constrained.cuh"
 #include "decode_mega.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -39,7 +40,7 @@
 using namespace gitb200;
 typedef __nv_bfloat16 bf16;
 
-#define GITB200_ABI_VERSION 4
+#define GITB200_ABI_VERSION 5
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -180,6 +181,13 @@ struct gitb200_engine {
   const int64_t* rp_tok = nullptr;
   const int32_t* rp_lens = nullptr;
   int rp_rows = 0, rp_stride = 0;
+  // vocabulary trie (gitb200_set_trie; sticky) and the uniforms of the next sampled generate (gitb200_set_sampling)
+  DevBuf trie_begin, trie_token, trie_child, trie_cursor;
+  int trie_nodes = 0;
+  const float* sample_u = nullptr;
+  int sample_steps = 0, sample_rows = 0;
+  float sample_temperature = 1.0f;
+  bool constrained = false;            // this call's greedy selection runs constrained_select_kernel
   int64_t* pend_tok_host = nullptr;  // host-buffer variant: results land here
 };
 

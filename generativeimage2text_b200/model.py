@@ -57,6 +57,83 @@ class GeneratorWithBeamSearch(object):
             raise NotImplementedError('repetition_penalty / temperature are not used by get_git_model')
 
 
+class TokenNode(object):
+    """Reference trie_decoder.py:220-222."""
+
+    def __init__(self):
+        self.children = {}
+
+
+class TokenTrie(object):
+    """Mirror of the reference's vocabulary trie (trie_decoder.py:224-258): same methods; `to_csr()` is what the engine
+    takes (include/gitb200.h gitb200_set_trie)."""
+
+    def __init__(self):
+        self.root = TokenNode()
+        self.curr = self.root
+
+    @classmethod
+    def construct(cls, all_tokens):
+        ret = cls()
+        for ts in all_tokens:
+            ret.insert(ts)
+        return ret
+
+    def insert(self, tokens):
+        cur = self.root
+        for t in tokens:
+            cur = cur.children.setdefault(int(t), TokenNode())
+
+    def get_valid(self, tokens):
+        r = self.root
+        for t in tokens:
+            r = r.children.get(int(t))
+            if r is None:
+                return []
+        return list(r.children.keys())
+
+    def reset(self):
+        self.curr = self.root
+
+    def get_curr_valid(self):
+        return list(self.curr.children.keys())
+
+    def move(self, t):
+        assert t in self.curr.children
+        self.curr = self.curr.children[t]
+
+    def to_csr(self):
+        """(child_begin [n_nodes + 1], child_token [n_edges], child_node [n_edges]) as int32 lists; node 0 = root,
+        nodes numbered breadth first, a node's edges in insertion order."""
+        nodes, begin, tok, child = [self.root], [0], [], []
+        index = {id(self.root): 0}
+        i = 0
+        while i < len(nodes):
+            for t, c in nodes[i].children.items():
+                if id(c) not in index:
+                    index[id(c)] = len(nodes)
+                    nodes.append(c)
+                tok.append(int(t))
+                child.append(index[id(c)])
+            begin.append(len(tok))
+            i += 1
+        return begin, tok, child
+
+
+class TrieAutoRegressiveBeamSearch(object):
+    """Search configuration mirroring reference trie_decoder.py:27-42 (the decoder model.py:42-48 keeps commented out):
+    greedy decoding restricted to the token sequences of `trie`.  The reference holds one trie cursor and constrains row 0
+    only; the engine gives every row of a batch its own cursor (each row = a batch-1 call of the reference)."""
+
+    def __init__(self, eos_index, max_steps=50, beam_size=5, trie=None):
+        self._eos_index = eos_index
+        self.max_steps = max_steps
+        assert beam_size == 1                                      # reference trie_decoder.py:38
+        self.beam_size = beam_size
+        self.per_node_beam_size = 1
+        self.trie = trie
+
+
 class _Pending(object):
     """Handle of an enqueued `model(batch)` (see GitB200CaptioningModel.submit)."""
 
@@ -256,7 +333,7 @@ class GitB200CaptioningModel(nn.Module):
         if sl['engine'] is None:
             h = ctypes.c_void_p()
             _lib.check(lib.gitb200_create(ctypes.byref(self._cfg), dev.index or 0, ctypes.byref(h)), None, 'create')
-            sl['engine'], sl['sig'] = h, None
+            sl['engine'], sl['sig'], sl['trie_key'] = h, None, None
             import os
             for opt in ('use_graph', 'use_pdl', 'use_chain', 'use_2cta', 'use_mega', 'mega_coop', 'tc_attn', 'debug_layers', 'parity'):
                 v = os.environ.get('GITB200_' + opt.upper())      # debugging switches, e.g. GITB200_USE_2CTA=0
@@ -295,7 +372,7 @@ class GitB200CaptioningModel(nn.Module):
         for sl in reversed(self._slots):   # borrowers before the owner of the weights
             if sl['engine'] is not None:
                 _lib.load().gitb200_destroy(sl['engine'])
-                sl['engine'], sl['sig'], sl['pending'] = None, None, None
+                sl['engine'], sl['sig'], sl['pending'], sl['trie_key'] = None, None, None, None
 
     def __del__(self):
         try:
@@ -332,13 +409,14 @@ class GitB200CaptioningModel(nn.Module):
 
     def _search_struct(self):
         d = self.decoder
-        if isinstance(d, AutoRegressiveBeamSearch):
+        if isinstance(d, (AutoRegressiveBeamSearch, TrieAutoRegressiveBeamSearch)):
             return _lib.Search(mode=_lib.SEARCH_GREEDY, max_steps=d.max_steps, beam_size=1, per_node_beam=1,
                                length_penalty=1.0)
         if isinstance(d, GeneratorWithBeamSearch):
             return _lib.Search(mode=_lib.SEARCH_BEAM, max_steps=d.max_steps, beam_size=d.beam_size,
                                per_node_beam=d.per_node_beam_size, length_penalty=float(d.length_penalty))
-        raise TypeError('model.decoder must be an AutoRegressiveBeamSearch or GeneratorWithBeamSearch of this package')
+        raise TypeError('model.decoder must be an AutoRegressiveBeamSearch, TrieAutoRegressiveBeamSearch or GeneratorWithBeamSearch '
+                        'of this package')
 
     def _pack_images(self, image):
         """-> (fp32 contiguous [frames*B,3,S,S] on device, B, frames) ; frames = 0 for a bare tensor."""
@@ -363,18 +441,23 @@ class GitB200CaptioningModel(nn.Module):
 
     # ---------------------------------------------------------------- the reference surface
     @torch.no_grad()
-    def forward(self, batch, forced_tokens=None, return_step_logits=False):
+    def forward(self, batch, forced_tokens=None, return_step_logits=False, search_param=None):
         """`model(batch)` of the reference in eval mode: CaptioningModel.forward -> infer.
 
         batch: {'image': FloatTensor[B,3,H,W] | [FloatTensor[B,3,H,W]] * frames, 'prefix'?: LongTensor[1,P]}
                (extension: 'prefix': LongTensor[B,P] + optional 'prefix_len': [B] = one prefix per image)
         forced_tokens / return_step_logits are parity-test hooks (teacher forcing, raw per-step logits).
+        search_param: the dict CaptioningModel.infer forwards to decoder.search (layers/decoder.py:999-1003); understood:
+               {'do_sample': True, 'temperature': T, 'top_k': ., 'top_p': .} with the greedy decoder -- top_k / top_p are
+               accepted and ignored exactly like the reference (its filter call is commented out, :372) -- plus
+               'uniforms': FloatTensor[max_steps, B] or 'generator': torch.Generator for the random numbers.
         """
-        return self.submit(batch, forced_tokens, return_step_logits, slot=0, _caller_stream=True).result()
+        return self.submit(batch, forced_tokens, return_step_logits, slot=0, _caller_stream=True,
+                           search_param=search_param).result()
 
     @torch.no_grad()
     def submit(self, batch, forced_tokens=None, return_step_logits=False, slot=None, depth=2, _caller_stream=False,
-               coalesce=1):
+               coalesce=1, search_param=None):
         """Enqueue `model(batch)` without waiting: returns a handle whose `.result()` gives the reference's output
         dict.  Successive submits rotate over `depth` engines / streams (each engine: one call in flight).
 
@@ -387,8 +470,10 @@ class GitB200CaptioningModel(nn.Module):
             raise NotImplementedError("batch without 'image' is not supported")
         if 'context' in batch:
             raise NotImplementedError("'context' batches are not produced by the reference inference path")
+        search_param = dict(search_param or {})
+        constrained = bool(search_param) or isinstance(self.decoder, TrieAutoRegressiveBeamSearch)
         if (int(coalesce) > 1 and slot is None and not _caller_stream and forced_tokens is None and not return_step_logits
-                and 'prefix' not in batch and 'prefix_len' not in batch):
+                and 'prefix' not in batch and 'prefix_len' not in batch and not constrained):
             return self._submit_coalesced(batch['image'], depth, int(coalesce))
         if self._open_group is not None:
             self._open_group.launch()         # keep the submission order
@@ -447,7 +532,8 @@ class GitB200CaptioningModel(nn.Module):
         if return_step_logits:
             rows = B * (sp.beam_size if sp.mode == _lib.SEARCH_BEAM else 1)
             step_logits = torch.zeros((sp.max_steps - max(P, 1), rows, VOCAB), dtype=torch.float32, device=dev)
-        for t in (x, prefix, forced, row_prefix, row_lens_dev):
+        uniforms = self._sampling_setup(search_param, sp, B, dev)
+        for t in (x, prefix, forced, row_prefix, row_lens_dev, uniforms):
             if t is not None and stream is not cur:
                 t.record_stream(stream)
         # inputs of another size than test_crop_size (MinMaxResizeForTest, reference inference.py:29-64): the engine
@@ -456,14 +542,60 @@ class GitB200CaptioningModel(nn.Module):
         if row_prefix is not None:
             _lib.check(lib.gitb200_set_row_prefixes(eng, row_prefix.data_ptr(), B, int(row_prefix.shape[1]), row_lens_dev.data_ptr()),
                        eng, 'set_row_prefixes')
+        self._trie_setup(lib, sl)
+        if uniforms is not None:
+            _lib.check(lib.gitb200_set_sampling(eng, uniforms.data_ptr(), int(uniforms.shape[0]), B,
+                                                float(search_param.get('temperature', 1))), eng, 'set_sampling')
         _lib.check(lib.gitb200_generate_async(
             eng, x.data_ptr(), B, frames, prefix.data_ptr() if prefix is not None else None, P,
             ctypes.byref(sp), forced.data_ptr() if forced is not None else None, tokens.data_ptr(),
             logprobs.data_ptr(), step_logits.data_ptr() if step_logits is not None else None,
             stream.cuda_stream), eng, 'generate')
-        pend = _Pending(self, slot, sp, P, tokens, logprobs, step_logits, (x, prefix, forced, row_prefix, row_lens_dev), row_lens)
+        pend = _Pending(self, slot, sp, P, tokens, logprobs, step_logits, (x, prefix, forced, row_prefix, row_lens_dev, uniforms), row_lens)
         sl['pending'] = pend
         return pend
+
+    def _sampling_setup(self, search_param, sp, B, dev):
+        """search_param of the reference's decoder.search (layers/decoder.py:224-232) -> the uniforms the engine draws with."""
+        if not search_param:
+            return None
+        unknown = set(search_param) - {'do_sample', 'temperature', 'top_k', 'top_p', 'num_return_sequences', 'uniforms',
+                                       'generator', 'only_return_best'}
+        if unknown:
+            raise TypeError('unknown search_param keys: %s' % sorted(unknown))
+        if not isinstance(self.decoder, AutoRegressiveBeamSearch):
+            raise NotImplementedError('search_param (sampling) is implemented for AutoRegressiveBeamSearch only')
+        if search_param.get('num_return_sequences', 1) != 1 or not search_param.get('only_return_best', True):
+            raise NotImplementedError('num_return_sequences > 1 / only_return_best=False are not implemented')
+        temperature = float(search_param.get('temperature', 1))
+        if not search_param.get('do_sample', False):
+            assert temperature == 1, 'temperature needs do_sample'         # reference layers/decoder.py:259-261
+            return None
+        if not temperature > 0:
+            raise ValueError('temperature must be positive')
+        u = search_param.get('uniforms')
+        if u is None:
+            u = torch.rand((sp.max_steps, B), dtype=torch.float32, device=dev, generator=search_param.get('generator'))
+        u = u.to(device=dev, dtype=torch.float32).contiguous()
+        if u.dim() != 2 or u.shape[0] < sp.max_steps or u.shape[1] != B:
+            raise ValueError("'uniforms' must be a [>= max_steps, B] tensor")
+        return u
+
+    def _trie_setup(self, lib, sl):
+        """Hand the decoder's trie to the engine (or remove the one it holds) -- once per (engine, trie object)."""
+        d = self.decoder
+        trie = d.trie if isinstance(d, TrieAutoRegressiveBeamSearch) else None
+        key = id(trie) if trie is not None else None
+        if sl.get('trie_key') == key:
+            return
+        eng = sl['engine']
+        if trie is None:
+            _lib.check(lib.gitb200_set_trie(eng, None, None, None, 0, 0), eng, 'set_trie')
+        else:
+            begin, tok, child = trie.to_csr()
+            arr = lambda v: (ctypes.c_int32 * max(len(v), 1))(*v)
+            _lib.check(lib.gitb200_set_trie(eng, arr(begin), arr(tok), arr(child), len(begin) - 1, len(tok)), eng, 'set_trie')
+        sl['trie_key'] = key
 
     def _submit_coalesced(self, image, depth, want):
         dev = self._device()

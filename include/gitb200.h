@@ -153,6 +153,24 @@ int gitb200_last_decode_ms(gitb200_engine* h, float* ms_out, int32_t* steps_out,
  * buffers must stay valid until the call has finished. */
 int gitb200_set_row_prefixes(gitb200_engine* h, const int64_t* prefix_dev, int rows, int stride, const int32_t* lens_dev);
 
+/* Replaces: TrieAutoRegressiveBeamSearch.search + TokenTrie                            trie_decoder.py:27-258
+ * (the vocabulary-constrained greedy decoder model.py:42-48 keeps commented out next to the default one).  The trie is
+ * passed in CSR form from HOST memory: node n's outgoing edges are [child_begin[n], child_begin[n + 1]), edge e accepts
+ * token child_token[e] and leads to node child_node[e]; node 0 is the root.  While a trie is set, GREEDY generate calls
+ * raise the log-probs of the allowed next tokens by (max logit - min logit + 1) before the top-1 (:61-62, :141-142),
+ * move the cursor (:70, :153) and accumulate the raised value (:163).  Every row of the batch owns a cursor (the
+ * reference has one and constrains row 0 only: it is a batch-1 decoder).  Sticky; n_nodes = 0 removes the trie. */
+int gitb200_set_trie(gitb200_engine* h, const int32_t* child_begin_host, const int32_t* child_token_host,
+                     const int32_t* child_node_host, int n_nodes, int n_edges);
+
+/* Replaces: the do_sample branches of AutoRegressiveBeamSearch.search            layers/decoder.py:260-272, 364-375
+ * for the NEXT greedy generate call: row r draws its token at caption length t from softmax(logits / temperature) by an
+ * inverse-CDF lookup in index order with uniforms_dev[t * rows + r] (fp32 [steps >= max_steps, rows == batch], device;
+ * torch.multinomial's random stream cannot be reproduced, the distribution is the same).  Log-probs as the reference
+ * computes them: tempered log-softmax at a row's first decision, un-tempered afterwards.  The buffer must stay valid
+ * until the call has finished. */
+int gitb200_set_sampling(gitb200_engine* h, const float* uniforms_dev, int steps, int rows, float temperature);
+
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t gitb200_launch_count(const gitb200_engine* h);
 /* Engine switches (defaults in parentheses): use_graph (1) CUDA-graph replay of the decode step, use_pdl (1) programmatic

@@ -276,6 +276,115 @@ def greedy_search(start, step, max_steps=40, eos=EOS, trace=None):
     return pred, lp / num_valid
 
 
+def trie_csr_children(csr, node):
+    """(tokens, child nodes) of `node` in the CSR form the engine takes (include/gitb200.h gitb200_set_trie)."""
+    begin, tok, child = csr
+    return tok[begin[node]:begin[node + 1]], child[begin[node]:begin[node + 1]]
+
+
+def trie_search(start, step, csr, max_steps=40, eos=EOS, per_row=True):
+    """TrieAutoRegressiveBeamSearch.search (trie_decoder.py:44-218; beam_size is asserted 1, :38): greedy decoding in which
+    the log-probs of the tokens the trie allows next are raised by (max logit - min logit + 1) before the top-1.
+
+    per_row=False is the reference verbatim: ONE cursor, only row 0 is raised (:61-62, :141-142) and moved (:70, :153), max /
+    min over the whole [B, V] matrix.  per_row=True is what the engine implements: every row owns a cursor and is treated as a
+    batch-1 call (max / min over its own row; a row that already ended with EOS is EOS-forced and keeps its cursor).  For
+    B = 1 both are the same thing."""
+    B, P = start.shape
+    cur = [0] * B
+
+    def raise_allowed(ls, z, rows):
+        for r in rows:
+            toks, _ = trie_csr_children(csr, cur[r])
+            if len(toks):
+                zz = z[r] if per_row else z
+                ls[r, torch.tensor(toks, dtype=torch.long)] += zz.max() - zz.min() + 1          # :62 / :142
+
+    def move(tok, rows):
+        for r in rows:
+            toks, kids = trie_csr_children(csr, cur[r])
+            t = int(tok[r])
+            assert t in toks, 'token %d is not allowed at node %d' % (t, cur[r])      # TokenTrie.move :257
+            cur[r] = kids[toks.index(t)]
+
+    rows0 = list(range(B)) if per_row else [0]
+    logits = step(start)                                                        # :58
+    ls = F.log_softmax(logits, dim=1)                                           # :59
+    raise_allowed(ls, logits, rows0)
+    lp, tok = ls.max(dim=1)                                                     # topk(1) :67
+    move(tok, rows0)
+    if bool((tok == eos).all()):                                                # :72-79
+        return tok[:, None], lp[:, None]
+    pred = torch.cat([start, tok[:, None]], dim=1)                              # :86
+    while pred.shape[1] < max_steps:                                            # :101
+        last = pred[:, -1]
+        if bool((last == eos).all()):                                           # :107
+            break
+        z = step(pred)
+        z = z.scatter(1, last[:, None], -10000.0)                               # :122
+        done = last == eos
+        if bool(done.any()):                                                    # :134-138
+            forced = torch.full_like(z, float('-inf'))
+            forced[:, eos] = 0.0
+            z = torch.where(done[:, None], forced, z)
+        ls = F.log_softmax(z, dim=1)                                            # :140
+        live = [r for r in rows0 if not bool(done[r])] if per_row else rows0
+        raise_allowed(ls, z, live)
+        slp, tok = ls.max(dim=1)                                                # :150
+        move(tok, live)
+        lp = lp + slp                                                           # :163, :190-199 (beam 1)
+        pred = torch.cat([pred, tok[:, None]], dim=1)
+    num_valid = (pred != eos).sum(dim=-1)                                       # :206-211
+    num_valid = num_valid + ((pred == eos).sum(dim=-1) > 0).long()
+    num_valid = (num_valid - P).clip(min=1)
+    return pred, lp / num_valid
+
+
+def inverse_cdf_draw(probs, u):
+    """One index per row of `probs` [B, V]: the first i with cumsum(probs)[i] > u * sum(probs) -- the draw the engine makes in
+    place of torch.multinomial (whose random stream cannot be reproduced); float64 accumulation."""
+    c = torch.cumsum(probs.double(), dim=1)
+    target = u.double() * c[:, -1]
+    idx = (c > target[:, None]).float().argmax(dim=1)
+    none = ~(c > target[:, None]).any(dim=1)
+    return torch.where(none, torch.full_like(idx, probs.shape[1] - 1), idx)
+
+
+def sample_search(start, step, uniforms, temperature=1.0, max_steps=40, eos=EOS, draw=inverse_cdf_draw):
+    """The do_sample=True branches of AutoRegressiveBeamSearch.search with beam_size = per_node_beam_size = 1
+    (layers/decoder.py:224-440): the first token is drawn from softmax(logits / T) and scored with log_softmax(logits / T)
+    (:259-272); later tokens are drawn from softmax(z / T) but scored with log_softmax(z) of the UN-tempered masked logits
+    (:358 before :369-370).  `uniforms[t, r]` drives the draw of row r at caption length t."""
+    B, P = start.shape
+    logits = step(start) / temperature                                          # :258-261
+    ls = F.log_softmax(logits, dim=1)                                           # :265
+    tok = draw(logits.softmax(dim=1), uniforms[P])                              # :274-275
+    lp = ls.gather(1, tok[:, None])[:, 0]                                       # :276
+    if bool((tok == eos).all()):                                                # :279-291
+        return tok[:, None], lp[:, None]
+    pred = torch.cat([start, tok[:, None]], dim=1)
+    while pred.shape[1] < max_steps:
+        last = pred[:, -1]
+        if bool((last == eos).all()):
+            break
+        z = step(pred)
+        z = z.scatter(1, last[:, None], -10000.0)                               # :330
+        done = last == eos
+        if bool(done.any()):                                                    # :347-351
+            forced = torch.full_like(z, float('-inf'))
+            forced[:, eos] = 0.0
+            z = torch.where(done[:, None], forced, z)
+        ls = F.log_softmax(z, dim=1)                                            # :358
+        tok = draw((z / temperature).softmax(dim=1), uniforms[pred.shape[1]])   # :369-373
+        tok = torch.where(done, torch.full_like(tok, eos), tok)                 # a one-hot distribution has one outcome
+        lp = lp + ls.gather(1, tok[:, None])[:, 0]                              # :374, :386
+        pred = torch.cat([pred, tok[:, None]], dim=1)
+    num_valid = (pred != eos).sum(dim=-1)                                       # :433-438
+    num_valid = num_valid + ((pred == eos).sum(dim=-1) > 0).long()
+    num_valid = (num_valid - P).clip(min=1)
+    return pred, lp / num_valid
+
+
 def _length_norm(length, lp):
     """BeamHypotheses._length_norm (layers/decoder.py:1310-1313)."""
     return (5 + length) ** lp / (5 + 1) ** lp

@@ -708,3 +708,92 @@ def test_prefix_batches_one_prefix_per_image(search):
             assert same
             assert abs(full['logprobs'].reshape(-1)[r].item() - one['logprobs'].reshape(-1)[0].item()) < 5e-2
     print('%s: %d rows had only decisive reference decisions' % (search, n_checked))
+
+
+# ---- the remaining decoders --------------------------------------------------------------------------------
+def _trie_from_reference_captions(pred, extra_seed=0):
+    """A vocabulary trie that contains the free-running greedy captions' first tokens plus decoys, so that the constraint
+    both binds and leaves real choices: sequences of 3-6 tokens ending in EOS."""
+    g = torch.Generator().manual_seed(extra_seed)
+    seqs = []
+    for row in pred.tolist():
+        body = [t for t in row[1:] if t != 102][:4]
+        seqs.append(body + [102])
+        for _ in range(6):                                   # decoys sharing a prefix of the row's own caption
+            cut = int(torch.randint(0, len(body) + 1, (1,), generator=g))
+            tail = torch.randint(1000, 30000, (int(torch.randint(1, 4, (1,), generator=g)),), generator=g).tolist()
+            seqs.append(body[:cut] + tail + [102])
+    for _ in range(40):
+        seqs.append(torch.randint(1000, 30000, (int(torch.randint(2, 6, (1,), generator=g)),), generator=g).tolist() + [102])
+    return seqs
+
+
+def test_trie_decoder_replays_the_reference_semantics():
+    """TrieAutoRegressiveBeamSearch (reference trie_decoder.py:27-218) on the device: the oracle's restatement (pinned
+    against the reference class in tests/test_oracle_vs_reference.py) run over the ENGINE's own step logits must give the
+    engine's tokens and log-probs exactly; every caption is a path of the trie; rows of a batch equal their batch-1 calls."""
+    from generativeimage2text_b200.model import TrieAutoRegressiveBeamSearch, TokenTrie
+    g = load_golden('base_greedy')
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    m = _model(meta, sd, max_steps=12)
+    free = m(_to_cuda(batch))['predictions'].cpu()
+    seqs = _trie_from_reference_captions(free)
+    trie = TokenTrie.construct(seqs)
+    m.decoder = TrieAutoRegressiveBeamSearch(102, max_steps=12, beam_size=1, trie=trie)
+    out = m(_to_cuda(batch), return_step_logits=True)
+    torch.cuda.synchronize()
+    z = out['step_logits'].cpu()
+    it = iter(range(z.shape[0]))
+    B = meta['batch']
+    start = torch.full((B, 1), 101, dtype=torch.long)
+    pred, lp = git_oracle.trie_search(start, lambda partial: z[next(it)], trie.to_csr(), max_steps=12)
+    own = out['predictions'].cpu()
+    print('trie captions:', own.tolist())
+    assert torch.equal(pred, own)
+    assert torch.allclose(lp, out['logprobs'].cpu(), rtol=1e-4, atol=2e-3)
+    for row in own.tolist():
+        body = row[1:]
+        cut = body.index(102) + 1 if 102 in body else len(body)
+        assert body[:cut] in seqs, body                      # the constraint binds
+    # a batch row == its own batch-1 call (each row owns a trie cursor), and the trie can be swapped / removed
+    one = m({'image': batch['image'][1:2].cuda()})
+    n = one['predictions'].shape[1]
+    assert torch.equal(one['predictions'].cpu()[0], own[1, :n]) and bool((own[1, n:] == 102).all())
+    from generativeimage2text_b200.model import AutoRegressiveBeamSearch
+    m.decoder = AutoRegressiveBeamSearch(102, max_steps=12, beam_size=1, per_node_beam_size=1, fix_missing_prefix=True)
+    again = m(_to_cuda(batch))['predictions'].cpu()
+    assert torch.equal(again, free)
+
+
+@pytest.mark.parametrize('temperature', [1.0, 0.7])
+def test_sampling_replays_the_reference_semantics(temperature):
+    """do_sample branches of AutoRegressiveBeamSearch.search (reference layers/decoder.py:260-276, 364-375): the oracle's
+    restatement (pinned against the reference with the same draws) over the ENGINE's step logits and uniforms gives the
+    engine's tokens (a draw that lands within fp32 rounding of a CDF step may differ: at most one row) and log-probs."""
+    g = load_golden('base_greedy')
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    m = _model(meta, sd, max_steps=14)
+    B = meta['batch']
+    u = torch.rand((14, B), generator=torch.Generator().manual_seed(21))
+    out = m(_to_cuda(batch), return_step_logits=True, search_param={'do_sample': True, 'temperature': temperature, 'uniforms': u})
+    torch.cuda.synchronize()
+    z = out['step_logits'].cpu()
+    own = out['predictions'].cpu()
+    # teacher-forced replay: feed the oracle the engine's own history so that one near-tie cannot derail the comparison
+    start = torch.full((B, 1), 101, dtype=torch.long)
+    it = iter(range(z.shape[0]))
+    pred, lp = git_oracle.sample_search(start, lambda partial: z[next(it)], u, temperature=temperature, max_steps=14)
+    same = (pred == own).all(dim=1)
+    print('sampled captions:', own.tolist(), 'rows identical to the replay:', same.tolist())
+    assert int(same.sum()) >= B - 1
+    assert torch.allclose(lp[same], out['logprobs'].cpu()[same], rtol=1e-4, atol=2e-3)
+    greedy = m(_to_cuda(batch))['predictions'].cpu()
+    assert not torch.equal(greedy[:, :own.shape[1]], own[:, :greedy.shape[1]])          # it does sample
+    # same uniforms -> same captions; a generator works too
+    out2 = m(_to_cuda(batch), search_param={'do_sample': True, 'temperature': temperature, 'uniforms': u})
+    assert torch.equal(out2['predictions'].cpu(), own)
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    out3 = m(_to_cuda(batch), search_param={'do_sample': True, 'temperature': temperature, 'generator': gen})
+    assert out3['predictions'].shape[0] == B

@@ -100,3 +100,33 @@ def test_search_configuration_classes_keep_the_reference_checks():
         M.GeneratorWithBeamSearch(EOS, max_steps=8, beam_size=4, length_penalty=0)
     with pytest.raises(NotImplementedError):
         M.GeneratorWithBeamSearch(EOS, max_steps=8, beam_size=4, temperature=0.7)
+
+
+def test_token_trie_mirror_and_csr():
+    """TokenTrie (reference trie_decoder.py:224-258) mirror: same answers as a plain prefix scan; CSR export round-trips."""
+    import random
+    from generativeimage2text_b200.model import TokenTrie, TrieAutoRegressiveBeamSearch
+    rnd = random.Random(4)
+    seqs = [[rnd.randrange(0, 12) for _ in range(rnd.randrange(1, 6))] + [102] for _ in range(60)]
+    trie = TokenTrie.construct(seqs)
+    for _ in range(200):
+        pre = rnd.choice(seqs)[:rnd.randrange(0, 5)]
+        want = sorted({s[len(pre)] for s in seqs if s[:len(pre)] == pre and len(s) > len(pre)})
+        assert sorted(trie.get_valid(pre)) == want
+    begin, tok, child = trie.to_csr()
+    assert begin[0] == 0 and begin[-1] == len(tok) == len(child)
+    for s in seqs:                                            # every sequence is a root-to-leaf walk of the CSR form
+        node = 0
+        for t in s:
+            edges = range(begin[node], begin[node + 1])
+            hit = [e for e in edges if tok[e] == t]
+            assert len(hit) == 1
+            node = child[hit[0]]
+    trie.reset()
+    trie.move(seqs[0][0])
+    assert sorted(trie.get_curr_valid()) == sorted(trie.get_valid(seqs[0][:1]))
+    d = TrieAutoRegressiveBeamSearch(102, max_steps=20, beam_size=1, trie=trie)
+    assert d.per_node_beam_size == 1 and d.trie is trie
+    import pytest
+    with pytest.raises(AssertionError):
+        TrieAutoRegressiveBeamSearch(102, max_steps=20, beam_size=2, trie=trie)      # reference trie_decoder.py:38

@@ -67,3 +67,11 @@ if len(fine) > 10:
             ph, sb = (k - 710000) // 100, (k - 710000) % 100
             print('  %-6s %-46s +%6.2f us' % (names[ph - 1], sub.get(sb, str(sb)), (t - prev) * ns_per_clk * 1e-3))
             prev = t
+        lm = sorted((t, k) for t, k in fine[10] if 720000 <= k < 730000)
+        if lm:
+            print('\nLM head of that step, thread 0 of CTA 0:')
+            what = {0: 'A loads issued', 1: 'tiles landed', 2: 'MMAs + exchange done', 3: 'statistics done'}
+            prev = lm[0][0]
+            for t, k in lm:
+                print('  pair at tile %2d  %-24s +%6.2f us' % ((k - 720000) % 100, what[(k - 720000) // 100], (t - prev) * ns_per_clk * 1e-3))
+                prev = t
