@@ -1266,7 +1266,9 @@ static int step_layers(gitb200_engine* h, Lane& ln_, const long long* tokens, co
       dim3 grid(std::min(h->attn_grid, ln_.nb * h->cfg.dec_heads));
       if (beam == 1) CK(launch_k(pdl, decode_attn_kernel<1, true>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
       else if (beam == 4) CK(launch_k(pdl, decode_attn_kernel<4>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
-      else return fail(h, "decode: beam size %d not supported (1 or 4)", beam);
+      else if (beam == 3) CK(launch_k(pdl, decode_attn_kernel<3>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+      else if (beam == 2) CK(launch_k(pdl, decode_attn_kernel<2>, grid, dim3(128), h->attn_smem, st, tk, tv, ap));
+      else return fail(h, "decode: beam size %d not supported (1 .. 4)", beam);
       CKL(h, "decode_attn_kernel");
       next_link(grid.x);
     }
@@ -1303,6 +1305,8 @@ static int set_attn_smem_limit(gitb200_engine* h) {
   h->attn_grid = std::min(items, per_sm * h->num_sms);
   CK(cudaFuncSetAttribute(decode_attn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
+  CK(cudaFuncSetAttribute(decode_attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
+  CK(cudaFuncSetAttribute(decode_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->attn_smem)));
   CK(h->chain.ensure(256));
   CK(cudaMemset(h->chain.p, 0, 256));
   return 0;

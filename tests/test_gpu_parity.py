@@ -797,3 +797,24 @@ def test_sampling_replays_the_reference_semantics(temperature):
     gen = torch.Generator(device='cuda').manual_seed(3)
     out3 = m(_to_cuda(batch), search_param={'do_sample': True, 'temperature': temperature, 'generator': gen})
     assert out3['predictions'].shape[0] == B
+
+
+@pytest.mark.parametrize('beam', [2, 3])
+def test_beam_sizes_other_than_the_default(beam):
+    """GeneratorWithBeamSearch with beam_size 2 / 3 (per-node 2; the shipped default is 4): exact replay of the oracle's
+    restatement over the engine's own step logits, as for the default size."""
+    from generativeimage2text_b200.model import GeneratorWithBeamSearch
+    g = load_golden('base_beam')
+    meta = g['meta']
+    sd, batch = golden_inputs(meta)
+    m = _model(meta, sd)
+    m.decoder = GeneratorWithBeamSearch(102, max_steps=meta['max_steps'], beam_size=beam, length_penalty=0.6)
+    out = m(_to_cuda(batch), return_step_logits=True)
+    torch.cuda.synchronize()
+    z = out['step_logits'].cpu()
+    assert z.shape[1] == meta['batch'] * beam
+    it = iter(range(z.shape[0]))
+    pred, lp = git_oracle.beam_search(torch.full((meta['batch'], 1), 101, dtype=torch.long),
+                                      lambda ids: z[next(it)], max_steps=meta['max_steps'], beam=beam)
+    assert torch.equal(pred, out['predictions'].cpu())
+    assert torch.allclose(lp, out['logprobs'].cpu(), atol=2e-3)
