@@ -470,6 +470,251 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// flash_attn_tc_long_kernel: the same attention on tcgen05 for sequences that do NOT fit the tensor memory in one piece
+// (S > 512: the 6-frame video prefill with 1182 keys, 30 x 40 VQA grids with 1201).
+//   One CTA per (head, batch, 128-row query tile), two CTAs per SM.  The keys are walked in blocks of 128, twice:
+//     pass 0:  S_blk = Q K_blk^T (tcgen05.mma into TMEM columns [0, 128))  ->  the softmax warps fold the block into the row maximum;
+//     pass 1:  S_blk again  ->  P_blk = exp2((S_blk - max) * scale) as bf16 in the K-major operand layout  ->
+//              O += P_blk V_blk (TMEM columns [128, 192), accumulated by the tensor core across the blocks).
+//   Recomputing S costs a second pass of QK^T MMAs -- the tensor pipe idles below 15 % in these kernels, the softmax warps'
+//   instruction issue is the limit -- and buys a softmax without running-maximum corrections of O (which would be a TMEM
+//   load / scale / store round trip per block).  K blocks are double buffered (the next block's TMA overlaps the current
+//   block's MMA and softmax), V and P single buffered; 192 of 256 allocated TMEM columns, 99 KB of shared memory.
+//   Warp 0: TMA + MMA issue (one lane); warps 1-8: softmax / epilogue, two per TMEM lane quadrant, splitting the 16-column
+//   chunks of a block like flash_attn_tc_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnLongBlk = 128;        // keys per block
+__host__ __device__ inline size_t attn_tc_long_smem_bytes() {
+  return 1024 + 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 128 /*barriers*/ + 2048 /*row max / row sum*/;
+}
+
+__global__ void __launch_bounds__(kAttnTcThreads, 2)
+flash_attn_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t attn_tcl_raw[];
+  uint8_t* smem = attn_tcl_raw + ((1024u - (smem_u32(attn_tcl_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;                  // two buffers of 16 KB
+  uint8_t* sV = smem + 3 * 16384;
+  uint8_t* sP = smem + 4 * 16384;              // two sub-blocks [128 rows x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * 16384);
+  uint64_t* bar_q = bars;          // Q tile landed (once)
+  uint64_t* bar_k = bars + 1;      // [2] K block landed
+  uint64_t* bar_v = bars + 3;      // V block landed
+  uint64_t* bar_s = bars + 4;      // S block complete in TMEM
+  uint64_t* bar_d = bars + 5;      // the 8 softmax warps are done with the S block (pass 1: and have written P)
+  uint64_t* bar_o = bars + 6;      // P V of the block complete: P and V shared memory may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* row_sums = reinterpret_cast<float*>(bars + 16);    // [2 halves][128 rows]
+  float* row_max = row_sums + 256;                          // [2 halves][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y, tile = blockIdx.z;
+  const int nblk = (p.S + kAttnLongBlk - 1) / kAttnLongBlk;
+  const int n_it = 2 * nblk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(bar_q, 1);
+    mbar_init(&bar_k[0], 1);
+    mbar_init(&bar_k[1], 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_d, 8);
+    mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kv_row0 = static_cast<int>(b * p.kv_rows_per_batch);
+      const uint32_t idesc_s = umma_idesc_bf16(128, kAttnLongBlk);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);     // B operand (V) is MN-major
+      mbar_arrive_expect_tx(bar_q, 16384);
+      tma_load_2d(sQ, &tmQ, bar_q, p.q_col0 + h * 64, static_cast<int>(b * p.q_rows_per_batch) + tile * 128);
+      mbar_arrive_expect_tx(&bar_k[0], 16384);
+      tma_load_2d(sK, &tmK, &bar_k[0], p.k_col0 + h * 64, kv_row0);
+      mbar_wait_lim(bar_q, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int pass = it >= nblk ? 1 : 0;
+        const int blk = it - pass * nblk;
+        const int buf = it & 1;
+        // the next iteration's K block (its buffer was last read by the S MMA of iteration it - 1, whose commit we waited for)
+        if (it + 1 < n_it) {
+          const int nb = (it + 1) - ((it + 1) >= nblk ? nblk : 0);
+          mbar_arrive_expect_tx(&bar_k[buf ^ 1], 16384);
+          tma_load_2d(sK + (buf ^ 1) * 16384, &tmK, &bar_k[buf ^ 1], p.k_col0 + h * 64, kv_row0 + nb * kAttnLongBlk);
+        }
+        if (pass == 1) {
+          if (blk > 0) mbar_wait_lim(bar_o, (blk - 1) & 1);       // the previous P V has finished reading V (and P)
+          mbar_arrive_expect_tx(bar_v, 16384);
+          tma_load_2d(sV, &tmV, bar_v, p.v_col0 + h * 64, kv_row0 + blk * kAttnLongBlk);
+        }
+        mbar_wait_lim(&bar_k[buf], (it >> 1) & 1);
+        if (it > 0) mbar_wait_lim(bar_d, (it - 1) & 1);           // the softmax warps have read the previous S block
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sQ) + k * 32), umma_desc_sw128(smem_u32(sK) + buf * 16384 + k * 32), idesc_s,
+                    k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        if (pass == 1) {
+          mbar_wait_lim(bar_v, blk & 1);
+          mbar_wait_lim(bar_d, it & 1);                           // P of this block written
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb)
+            umma_bf16(tmem_o, umma_desc_sw128(smem_u32(sP) + (kb >> 2) * 16384 + (kb & 3) * 32),
+                      umma_desc_sw128(smem_u32(sV) + kb * 2048), idesc_pv, (blk > 0 || kb > 0) ? 1u : 0u);
+          umma_commit(bar_o);
+        } else {
+          mbar_wait_lim(bar_s, it & 1);                           // (so that the K buffer is free for the prefetch above)
+        }
+      }
+    }
+  } else {
+    // ---- softmax / epilogue: thread = query row = TMEM lane; the two warps of a quadrant split the 16-column chunks ----
+    const int quad = warp & 3;
+    const int half = (warp - 1) >> 2;
+    const int row = quad * 32 + lane;                 // row of the tile
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    // ---- pass 0: the row maximum over all key blocks ----
+    float mx = -INFINITY;
+    for (int blk = 0; blk < nblk; ++blk) {
+      mbar_wait_lim(bar_s, blk & 1);
+      tc_fence_after();
+      const int valid = min(kAttnLongBlk, p.S - blk * kAttnLongBlk);      // keys of this block that exist
+      const int n_full = valid >> 4;
+      for (int c = half; c < 8; c += 4) {
+        uint32_t ra[16], rb[16];
+        tmem_ld_32x32b_x16(t_lane + c * 16, ra);
+        tmem_ld_32x32b_x16(t_lane + (c + 2) * 16, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const uint32_t (&r)[16] = w ? rb : ra;
+          const int cc = c + 2 * w;
+          if (cc < n_full) {
+            float m0 = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3])));
+            float m1 = fmaxf(fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
+            m0 = fmaxf(m0, fmaxf(fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])), fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11]))));
+            m1 = fmaxf(m1, fmaxf(fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])), fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15]))));
+            mx = fmaxf(mx, fmaxf(m0, m1));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cc * 16 + j < valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d);
+    }
+    row_max[half * 128 + row] = mx;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+    mx = fmaxf(mx, row_max[(half ^ 1) * 128 + row]);
+    // ---- pass 1: P blocks and the partial row sum ----
+    float sum = 0.f;
+    const float mb = mx * p.scale_log2;
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int it = nblk + blk;
+      mbar_wait_lim(bar_s, it & 1);
+      if (blk > 0) mbar_wait_lim(bar_o, (blk - 1) & 1);           // the previous P V has finished reading P
+      tc_fence_after();
+      const int valid = min(kAttnLongBlk, p.S - blk * kAttnLongBlk);
+      const int n_full = valid >> 4;
+      for (int c = half; c < 8; c += 4) {
+        uint32_t ra[16], rb[16];
+        tmem_ld_32x32b_x16(t_lane + c * 16, ra);
+        tmem_ld_32x32b_x16(t_lane + (c + 2) * 16, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const uint32_t (&r)[16] = w ? rb : ra;
+          const int cc = c + 2 * w;
+          uint32_t pk[8];
+          float s0 = 0.f, s1 = 0.f;
+          if (cc < n_full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mb));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mb));
+              s0 += p0;
+              s1 += p1;
+              pk[j] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float p0 = (cc * 16 + 2 * j < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mb)) : 0.f;
+              const float p1 = (cc * 16 + 2 * j + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mb)) : 0.f;
+              s0 += p0;
+              s1 += p1;
+              pk[j] = pack_bf16(p0, p1);
+            }
+          }
+          sum += s0 + s1;
+          uint8_t* pb = sP + (cc >> 2) * 16384 + row * 128;
+          const int ch = 2 * (cc & 3);
+          *reinterpret_cast<uint4*>(pb + (((ch) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(pb + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d);
+    }
+    row_sums[half * 128 + row] = sum;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+    const float inv = 1.0f / (row_sums[row] + row_sums[128 + row]);
+    // ---- O / row sum -> bf16 row (each warp: two of the four 16-column chunks) ----
+    mbar_wait_lim(bar_o, (nblk - 1) & 1);
+    tc_fence_after();
+    const int qrow = tile * 128 + row;
+    __nv_bfloat16* orow = p.out + b * p.o_bs + static_cast<long long>(qrow) * p.o_rs + h * 64;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = 2 * cc + half;
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_lane + 128 + c * 16, r);
+      tmem_ld_wait();
+      if (qrow < p.S) {
+        uint4 v0, v1;
+        v0.x = pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+        v0.y = pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+        v0.z = pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+        v0.w = pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+        v1.x = pack_bf16(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+        v1.y = pack_bf16(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+        v1.z = pack_bf16(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+        v1.w = pack_bf16(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+        reinterpret_cast<uint4*>(orow + c * 16)[0] = v0;
+        reinterpret_cast<uint4*>(orow + c * 16)[1] = v1;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct DecAttnParams {
   const float* qkv;                // [n_partials][R, 3*D] fp32 (q | k | v): the QKV GEMM's split-K partial sums, added
   int n_partials;                  //   here in split order (1..4 buffers, partial_stride elements apart)

@@ -536,11 +536,39 @@ static int launch_attention_tc(gitb200_engine* h, const AttnParams& ap, cudaStre
   return 0;
 }
 
+// tcgen05 attention for sequences beyond the tensor memory (attention.cuh: flash_attn_tc_long_kernel): 128-key blocks, two passes
+static int launch_attention_tc_long(gitb200_engine* h, const AttnParams& ap, cudaStream_t st) {
+  AttnTcParams p{};
+  p.out = ap.out; p.B = ap.B; p.S = ap.S; p.H = ap.H;
+  p.spad = (ap.S + 15) / 16 * 16;
+  p.kv_boxes = 1; p.kv_box_rows = kAttnLongBlk;
+  p.q_rows_per_batch = ap.S; p.kv_rows_per_batch = ap.S;
+  p.q_col0 = 0; p.k_col0 = 0; p.v_col0 = 0;
+  p.o_rs = ap.o_rs; p.o_bs = ap.o_bs;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  const long long rows = static_cast<long long>(ap.B) * ap.S;
+  CUtensorMap tq, tk, tv;
+  TRY(get_tmap(h, ap.q, rows, ap.H * 64, ap.q_rs, 128, &tq));
+  TRY(get_tmap(h, ap.k, rows, ap.H * 64, ap.kv_rs, kAttnLongBlk, &tk));
+  TRY(get_tmap(h, ap.v, rows, ap.H * 64, ap.kv_rs, kAttnLongBlk, &tv));
+  const size_t smem = attn_tc_long_smem_bytes();
+  static bool attr_done[64] = {false};
+  if (!attr_done[h->device & 63]) {
+    CK(cudaFuncSetAttribute(flash_attn_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done[h->device & 63] = true;
+  }
+  flash_attn_tc_long_kernel<<<dim3(ap.H, ap.B, (ap.S + 127) / 128), kAttnTcThreads, smem, st>>>(tq, tk, tv, p);
+  CKL(h, "flash_attn_tc_long_kernel");
+  return 0;
+}
+
 static int launch_attention(gitb200_engine* h, const AttnParams& ap, cudaStream_t st) {
   if (h->tc_attn && ap.S <= 512 && ap.q_bs == static_cast<long long>(ap.S) * ap.q_rs && ap.kv_bs == static_cast<long long>(ap.S) * ap.kv_rs &&
       attn_tc_smem_bytes((ap.S + 15) / 16 * 16, ap.S <= 256 ? (ap.S + 15) / 16 * 16 : (((ap.S + 15) / 16 * 16 + 1) / 2 + 7) / 8 * 8,
                          ap.S <= 256 ? 1 : 2) <= 226 * 1024)
     return launch_attention_tc(h, ap, st);
+  if (h->tc_attn && ap.S > 512 && ap.q_bs == static_cast<long long>(ap.S) * ap.q_rs && ap.kv_bs == static_cast<long long>(ap.S) * ap.kv_rs)
+    return launch_attention_tc_long(h, ap, st);
   AttnParams p = ap;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   // query rows per CTA = 16 * NW: least padding first, then the larger tile (K/V are re-read per query tile)

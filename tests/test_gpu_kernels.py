@@ -135,7 +135,8 @@ def test_layernorm(D, rows):
     assert (ob.float() - ref).abs().max().item() < 3e-2
 
 
-@pytest.mark.parametrize('B,S,H', [(2, 197, 12), (1, 257, 16), (1, 64, 1), (1, 1182, 12), (3, 5, 2)])
+@pytest.mark.parametrize('B,S,H', [(2, 197, 12), (1, 257, 16), (1, 64, 1), (1, 1182, 12), (3, 5, 2), (2, 513, 3), (1, 640, 2),
+                                   (2, 1201, 12), (3, 600, 1)])
 def test_flash_attention(B, S, H):
     L = _lib()
     d = H * 64
