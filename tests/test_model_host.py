@@ -130,3 +130,46 @@ def test_token_trie_mirror_and_csr():
     import pytest
     with pytest.raises(AssertionError):
         TrieAutoRegressiveBeamSearch(102, max_steps=20, beam_size=2, trie=trie)      # reference trie_decoder.py:38
+
+
+def test_search_param_validation_mirrors_the_reference_signature():
+    """`search_param` is what CaptioningModel.infer forwards to decoder.search (reference layers/decoder.py:999-1003, 224-232):
+    the host-side checks of `_sampling_setup`, on the CPU (no engine is touched)."""
+    import types
+    from generativeimage2text_b200 import _lib
+
+    class Tok:
+        cls_token_id, sep_token_id = 101, 102
+    m = M.get_git_model(Tok(), {})
+    sp = _lib.Search(mode=_lib.SEARCH_GREEDY, max_steps=12, beam_size=1, per_node_beam=1, length_penalty=1.0)
+    cpu = torch.device('cpu')
+    m.decoder = M.AutoRegressiveBeamSearch(EOS, max_steps=12, beam_size=1, per_node_beam_size=1, fix_missing_prefix=True)
+    assert m._sampling_setup({}, sp, 3, cpu) is None
+    assert m._sampling_setup({'do_sample': False}, sp, 3, cpu) is None
+    u = m._sampling_setup({'do_sample': True, 'temperature': 0.7, 'top_k': 5, 'top_p': 0.9}, sp, 3, cpu)     # top_k / top_p: ignored
+    assert tuple(u.shape) == (12, 3) and u.dtype == torch.float32 and bool(((u >= 0) & (u < 1)).all())
+    g1 = m._sampling_setup({'do_sample': True, 'generator': torch.Generator().manual_seed(7)}, sp, 3, cpu)
+    g2 = m._sampling_setup({'do_sample': True, 'generator': torch.Generator().manual_seed(7)}, sp, 3, cpu)
+    assert torch.equal(g1, g2)
+    mine = torch.rand(14, 3)
+    assert m._sampling_setup({'do_sample': True, 'uniforms': mine}, sp, 3, cpu) is not None
+    with pytest.raises(ValueError):
+        m._sampling_setup({'do_sample': True, 'uniforms': torch.rand(5, 3)}, sp, 3, cpu)          # fewer than max_steps rows
+    with pytest.raises(ValueError):
+        m._sampling_setup({'do_sample': True, 'temperature': 0.0}, sp, 3, cpu)
+    with pytest.raises(AssertionError):
+        m._sampling_setup({'temperature': 0.5}, sp, 3, cpu)                                        # reference :259-261
+    with pytest.raises(TypeError):
+        m._sampling_setup({'do_sample': True, 'beam_width': 3}, sp, 3, cpu)
+    with pytest.raises(NotImplementedError):
+        m._sampling_setup({'do_sample': True, 'num_return_sequences': 2}, sp, 3, cpu)
+    m.decoder = M.GeneratorWithBeamSearch(EOS, max_steps=12, beam_size=4, length_penalty=0.6)
+    with pytest.raises(NotImplementedError):
+        m._sampling_setup({'do_sample': True}, sp, 3, cpu)
+    # the trie decoder maps onto the greedy search mode of the engine
+    m.decoder = M.TrieAutoRegressiveBeamSearch(EOS, max_steps=9, beam_size=1, trie=M.TokenTrie.construct([[5, EOS]]))
+    s2 = m._search_struct()
+    assert s2.mode == _lib.SEARCH_GREEDY and s2.max_steps == 9 and s2.beam_size == 1
+    m.decoder = types.SimpleNamespace()
+    with pytest.raises(TypeError):
+        m._search_struct()
